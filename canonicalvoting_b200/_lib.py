@@ -1,0 +1,71 @@
+"""ctypes binding of the C ABI in include/cvb200.h (libcvb200.so).  Product path:
+fails loudly when the CUDA library is missing -- there is no CPU / PyTorch fallback."""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "_C", "libcvb200.so")
+
+_f = ctypes.c_void_p   # device float*
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_F3 = ctypes.c_float * 3
+_I3 = ctypes.c_int32 * 3
+
+# name -> (restype, argtypes); must list every symbol include/cvb200.h declares
+SIGNATURES = {
+    "cvb200_abi_version": (ctypes.c_int, []),
+    "cvb200_last_error": (ctypes.c_char_p, []),
+    "cvb200_hv_grid_dims_work_bytes": (ctypes.c_size_t, []),
+    "cvb200_hv_grid_dims": (ctypes.c_int, [_f, _i64, ctypes.c_float, _vp, ctypes.POINTER(ctypes.c_float),
+                                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32), _vp]),
+    "cvb200_hv_forward_work_bytes": (ctypes.c_size_t, [ctypes.POINTER(_i32)]),
+    "cvb200_hv_forward": (ctypes.c_int, [_f, _f, _f, _f, _i64, ctypes.c_float, _i32, ctypes.POINTER(ctypes.c_float),
+                                          ctypes.POINTER(_i32), _f, _f, _f, _vp, ctypes.c_size_t, _vp]),
+    "cvb200_hv_backward": (ctypes.c_int, [_f, _f, _f, _f, _f, _i64, ctypes.c_float, _i32,
+                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32), _f, _f, _f, _vp]),
+    "cvb200_hv_vote_indices": (ctypes.c_int, [_f, _f, _f, _i64, ctypes.c_float, _i32, ctypes.POINTER(ctypes.c_float),
+                                               ctypes.POINTER(_i32), _vp, _vp]),
+    "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
+}
+
+_lib = None
+
+
+class CVB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcvb200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CVB200Error(
+            "canonicalvoting_b200: %s is missing -- build it with `python -m canonicalvoting_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.cvb200_abi_version() != 1:
+        raise CVB200Error("libcvb200.so ABI version %d != 1 (stale build?)" % L.cvb200_abi_version())
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cvb200_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg))
+
+
+def f3(v):
+    return _F3(float(v[0]), float(v[1]), float(v[2]))
+
+
+def i3(v):
+    return _I3(int(v[0]), int(v[1]), int(v[2]))

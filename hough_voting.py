@@ -1,0 +1,2 @@
+"""`import hough_voting` -- op names used by BASELINE.json's north_star (vote / back_project)."""
+from canonicalvoting_b200.hough_voting import HoughVoting, HVFunction, vote, vote_host  # noqa: F401

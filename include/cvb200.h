@@ -1,0 +1,99 @@
+/*
+ * include/cvb200.h -- C ABI of libcvb200.so, the B200 (sm_100a) implementation of the
+ * CanonicalVoting hot path.  Plain pointers and sizes only: no torch / C++ types.
+ *
+ * Every entry point below is what a binding for the corresponding reference
+ * interface would call; the reference interface it replaces is cited as
+ * (file:line) relative to the qq456cvb/CanonicalVoting tree.
+ *
+ * Conventions
+ *   - all `d_*` pointers are DEVICE pointers on the current CUDA device, float32 /
+ *     int32, row-major contiguous (the reference enforces contiguity with
+ *     CHECK_CONTIGUOUS, houghvoting/src/hv_cuda.cpp:26-28);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream, which
+ *     is what the reference launches on, hv_cuda_kernel.cu:143);
+ *   - every function returns 0 on success, a positive cudaError_t on a CUDA
+ *     failure, or a negative CVB200_E* code on an argument error;
+ *     cvb200_last_error() returns a thread-local human-readable message;
+ *   - functions are asynchronous with respect to the host unless stated otherwise.
+ */
+#ifndef CVB200_H_
+#define CVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB200_ABI_VERSION 1
+
+#define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
+#define CVB200_ESCRATCH (-2) /* workspace too small */
+#define CVB200_EEMPTY   (-3) /* empty input where the reference would fail too */
+
+int cvb200_abi_version(void);
+const char *cvb200_last_error(void);
+
+/* ------------------------------------------------------------------ vote op ---- */
+
+/* Grid geometry of one scene: corner = min(points, 0), dims = int((max-min)/res)+1
+ * evaluated in float32 exactly like the reference host code
+ * (houghvoting/src/hv_cuda_kernel.cu:129-134,151).  SYNCHRONOUS: one device
+ * reduction + one 48-byte D->H copy + stream sync (the reference does 12 blocking
+ * .item() calls for the same information).
+ *   d_points   [n,3]
+ *   d_work     >= cvb200_hv_grid_dims_work_bytes() bytes of device scratch
+ *   h_corner   [3] out (host), h_maxpt [3] out (host, may be NULL), h_dims [3] out (host) */
+size_t cvb200_hv_grid_dims_work_bytes(void);
+int cvb200_hv_grid_dims(const float *d_points, int64_t n, float res, void *d_work,
+                        float *h_corner, float *h_maxpt, int32_t *h_dims, void *stream);
+
+/* Bytes of the interleaved accumulation workspace for a grid of X*Y*Z voxels.
+ * CONTRACT: the workspace must be all-zero when cvb200_hv_forward is entered and is
+ * all-zero again when the call's work completes (the write-out pass re-zeroes it),
+ * so a caller zero-fills it once after allocation and may then reuse it forever
+ * on the same stream. */
+size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]);
+
+/* hv_cuda.forward (houghvoting/src/hv_cuda.cpp:30-45 -> hv_cuda_kernel.cu:121-165):
+ * scatter every point's num_rots oriented centre votes into the grid with trilinear
+ * weights (hv_cuda_forward_kernel, :12-97) and divide grid_rot / grid_scale by
+ * (grid_obj + 1e-7) (hv_cuda_average_kernel, :100-119).
+ *   d_points,d_xyz,d_scale [n,3]; d_obj [n]
+ *   corner[3], dims[3]     host values (from cvb200_hv_grid_dims or the caller)
+ *   d_grid_obj [X,Y,Z], d_grid_rot [X,Y,Z,2], d_grid_scale [X,Y,Z,3]: outputs, every
+ *       element is written (no pre-zeroing needed; the reference needs 3 memsets)
+ *   d_work / work_bytes    see cvb200_hv_forward_work_bytes */
+int cvb200_hv_forward(const float *d_points, const float *d_xyz, const float *d_scale, const float *d_obj,
+                      int64_t n, float res, int32_t num_rots, const float corner[3], const int32_t dims[3],
+                      float *d_grid_obj, float *d_grid_rot, float *d_grid_scale,
+                      void *d_work, size_t work_bytes, void *stream);
+
+/* hv_cuda.backward (houghvoting/src/hv_cuda.cpp:47-71 -> hv_cuda_kernel.cu:265-302,
+ * kernel :168-261): gradient of sum(grad_grid * grid_obj) w.r.t. xyz / scale / obj.
+ * Faithful to the reference: only dL/dgrid_obj is consumed, the 1/res factor of the
+ * grid coordinate is not applied.  Outputs are fully overwritten.
+ *   d_grad_grid [X,Y,Z]; d_dxyz,d_dscale [n,3]; d_dobj [n] */
+int cvb200_hv_backward(const float *d_grad_grid, const float *d_points, const float *d_xyz,
+                       const float *d_scale, const float *d_obj, int64_t n, float res, int32_t num_rots,
+                       const float corner[3], const int32_t dims[3],
+                       float *d_dxyz, float *d_dscale, float *d_dobj, void *stream);
+
+/* Verification aid (no reference counterpart): the integer floor voxel of every vote,
+ * d_vote_idx [n,num_rots,3] int32, (-1,-1,-1) for votes the bounds test drops
+ * (hv_cuda_kernel.cu:41-45).  This is the bit-exact part of the op. */
+int cvb200_hv_vote_indices(const float *d_points, const float *d_xyz, const float *d_scale, int64_t n,
+                           float res, int32_t num_rots, const float corner[3], const int32_t dims[3],
+                           int32_t *d_vote_idx, void *stream);
+
+/* cos/sin of theta_i = i * (2*3.141592654f / num_rots) as the device evaluates them
+ * (hv_cuda_kernel.cu:35-38); d_cos,d_sin [num_rots].  Lets a CPU checker share the
+ * exact table. */
+int cvb200_hv_theta_table(int32_t num_rots, float *d_cos, float *d_sin, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVB200_H_ */
