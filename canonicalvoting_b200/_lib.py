@@ -30,6 +30,7 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
+ABI_VERSION = 3
 _lib = None
 
 
@@ -51,8 +52,8 @@ def load():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.cvb200_abi_version() != 1:
-        raise CVB200Error("libcvb200.so ABI version %d != 1 (stale build?)" % L.cvb200_abi_version())
+    if L.cvb200_abi_version() != ABI_VERSION:
+        raise CVB200Error("libcvb200.so ABI version %d != %d (stale build?)" % (L.cvb200_abi_version(), ABI_VERSION))
     _lib = L
     return L
 

@@ -4,15 +4,9 @@
 //   hv_cuda_forward_kernel / hv_cuda_average_kernel / hv_cuda_forward
 //   (houghvoting/src/hv_cuda_kernel.cu:12-97, :100-119, :121-165)
 //   hv_cuda_backward_kernel / hv_cuda_backward (:168-261, :265-302)
-// with a different decomposition (see DESIGN.md "vote op"):
-//   * one work item per (point, theta) instead of one thread per point with a serial
-//     theta loop; the cos/sin table is evaluated once per CTA into shared memory;
-//   * the six output channels of a voxel are accumulated in ONE 32-byte sector of an
-//     interleaved workspace [G][8] with vector reductions (red.global.add.v4/.v2.f32):
-//     16 REDs per vote instead of the reference's 48 scalar atomics to three tensors;
-//   * one fused write-out pass normalises (the reference's average kernel), splits the
-//     sector into the three API tensors with fully coalesced stores, and re-zeroes
-//     the workspace, so neither outputs nor workspace ever need a memset.
+// with a different decomposition (see DESIGN.md "vote op" and the "forward" section below):
+// a counting sort of the votes by grid cell followed by a per-voxel gather, instead of 48
+// float atomics per vote; outputs are written exactly once and never memset.
 //
 // Float contract: the integer voxel index of a vote must be bit-identical to the
 // reference's sm_100 build.  vote_center() spells out that build's exact operation
@@ -67,18 +61,20 @@ __device__ __forceinline__ bool vote_in_bounds(float gx, float gy, float gz, con
            gz < (float)(g.Z - 1);
 }
 
+// ------------------------------------------------------------------ forward ------
+// Workspace sector of voxel v: work[8v + {0:obj, 1:rot_cos, 2:rot_sin, 3:scale0, 4:scale1, 5:scale2, 6,7: unused}]
+// (A counting-sort + per-voxel gather formulation without float atomics, and a variant of this one with
+// per-block "touched" flags that lets the write-out skip untouched workspace, were built and measured:
+// profiles/exp_*; both are slower -- see DESIGN.md "what was tried".)
+constexpr int kScatterThreads = 256;
+constexpr int kPtsPerBlock = 64;   // power of two >= 32: a warp = 32 consecutive points, one theta
+
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b));
 }
-
-// ------------------------------------------------------------------ scatter ------
-// Workspace sector of voxel v: work[8v + {0:obj, 1:rot_cos, 2:rot_sin, 3:scale0, 4:scale1, 5:scale2, 6,7: unused}]
-constexpr int kScatterThreads = 256;
-constexpr int kPtsPerBlock = 64;  // power of two >= 32: a warp = 32 consecutive points, one theta
 
 __global__ void __launch_bounds__(kScatterThreads)
 hv_scatter_kernel(const float *__restrict__ points, const float *__restrict__ xyz, const float *__restrict__ scale,
@@ -130,17 +126,18 @@ hv_scatter_kernel(const float *__restrict__ points, const float *__restrict__ xy
         const float wx0 = 1.f - rx, wy0 = 1.f - ry, wz0 = 1.f - rz;
         const float objness = s_o[t];
         const float s0 = s_s[3 * t], s1 = s_s[3 * t + 1], s2 = s_s[3 * t + 2];
-        float *base = work + 8 * ((int64_t)fx * YZ + (int64_t)fy * g.Z + fz);
+        const int64_t v0 = (int64_t)fx * YZ + (int64_t)fy * g.Z + fz;
 #pragma unroll
         for (int a = 0; a < 2; a++) {
 #pragma unroll
             for (int b = 0; b < 2; b++) {
                 const float wxy = __fmul_rn(a ? rx : wx0, b ? ry : wy0);
+                const int64_t vab = v0 + (int64_t)a * YZ + (int64_t)b * g.Z;
 #pragma unroll
                 for (int d = 0; d < 2; d++) {
                     // ((wx*wy)*wz)*objness, the reference's association (:52-59)
                     const float w = __fmul_rn(__fmul_rn(wxy, d ? rz : wz0), objness);
-                    float *sec = base + 8 * ((int64_t)a * YZ + (int64_t)b * g.Z + d);
+                    float *sec = work + 8 * (vab + d);
                     red_add_v4(sec, w, __fmul_rn(w, cs), __fmul_rn(w, sn), __fmul_rn(w, s0));
                     red_add_v2(sec + 4, __fmul_rn(w, s1), __fmul_rn(w, s2));
                 }
@@ -150,45 +147,77 @@ hv_scatter_kernel(const float *__restrict__ points, const float *__restrict__ xy
 }
 
 // ------------------------------------------------------------------ write-out ----
-// Reference average kernel (:100-119): x /= (w + 1e-7) with a DOUBLE literal, i.e.
-// float(double(x) / (double(w) + 1e-7)).  x == 0 (the overwhelmingly common case in a
-// sparse grid) short-cuts to x, which is what the division returns for any positive
-// denominator.
-__device__ __forceinline__ float avg_div(float x, double den) {
-    if (x == 0.f && den > 0.0) return x;
-    return (float)((double)x / den);
+// x / (w + 1e-7) as the reference average kernel evaluates it (:100-119): the literal is a double, so the
+// quotient is float(double(x) / (double(w) + 1e-7)).  One reciprocal per voxel and a Markstein correction
+// step per channel give the correctly rounded double quotient (which is then rounded to float).
+__device__ __forceinline__ void avg_voxel(const float4 a, const float4 b, float &rc, float &rs, float &s0, float &s1,
+                                          float &s2) {
+    rc = rs = s0 = s1 = s2 = 0.f;
+    if (a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f && b.x == 0.f && b.y == 0.f) return;
+    const double den = (double)a.x + 1e-7;
+    if (!(fabs(den) > 1e-300 && fabs(den) < 1e300)) {   // degenerate denominators: plain IEEE division
+        rc = (float)((double)a.y / den); rs = (float)((double)a.z / den);
+        s0 = (float)((double)a.w / den); s1 = (float)((double)b.x / den); s2 = (float)((double)b.y / den);
+        return;
+    }
+    const double r = __drcp_rn(den);
+    auto div = [&](float xf) {
+        const double x = (double)xf;
+        const double q0 = x * r;
+        const double e = __fma_rn(-den, q0, x);
+        return (float)__fma_rn(e, r, q0);
+    };
+    rc = div(a.y); rs = div(a.z); s0 = div(a.w); s1 = div(b.x); s2 = div(b.y);
 }
 
 constexpr int kFinalizeThreads = 256;
+constexpr int kVoxPerThread = 4;
 
+// One thread = 4 consecutive voxels: 8 x 16-byte workspace loads, 8 x 16-byte zero stores (the workspace is
+// left all-zero for the next call) and 6 x 16-byte streaming output stores.
 __global__ void __launch_bounds__(kFinalizeThreads)
-hv_finalize_kernel(float4 *__restrict__ work, int64_t G, float *__restrict__ grid_obj,
-                   float2 *__restrict__ grid_rot, float *__restrict__ grid_scale) {
-    __shared__ __align__(16) float s_scale[3 * kFinalizeThreads];
-    const int64_t v0 = (int64_t)blockIdx.x * kFinalizeThreads;
-    const int64_t v = v0 + threadIdx.x;
-    if (v < G) {
-        const float4 a = work[2 * v];
-        const float4 b = work[2 * v + 1];
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        work[2 * v] = z;  // leave the workspace all-zero for the next call
-        work[2 * v + 1] = z;
-        const double den = (double)a.x + 1e-7;
-        __stcs(grid_obj + v, a.x);
-        __stcs(grid_rot + v, make_float2(avg_div(a.y, den), avg_div(a.z, den)));
-        s_scale[3 * threadIdx.x] = avg_div(a.w, den);
-        s_scale[3 * threadIdx.x + 1] = avg_div(b.x, den);
-        s_scale[3 * threadIdx.x + 2] = avg_div(b.y, den);
-    }
-    __syncthreads();
-    const int64_t rem = G - v0;
-    float *dst = grid_scale + 3 * v0;
-    if (rem >= kFinalizeThreads && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-        if (threadIdx.x < 3 * kFinalizeThreads / 4)
-            __stcs(reinterpret_cast<float4 *>(dst) + threadIdx.x, reinterpret_cast<float4 *>(s_scale)[threadIdx.x]);
+hv_finalize_kernel(float4 *__restrict__ work, int64_t G, float *__restrict__ grid_obj, float *__restrict__ grid_rot,
+                   float *__restrict__ grid_scale) {
+    const int64_t v = ((int64_t)blockIdx.x * kFinalizeThreads + threadIdx.x) * kVoxPerThread;
+    if (v >= G) return;
+    float o4[4] = {0.f, 0.f, 0.f, 0.f}, r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+          s12[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int nv = (int)min((int64_t)kVoxPerThread, G - v);
+    float4 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (j < nv) {
+            a[j] = __ldcs(work + 2 * (v + j));
+            b[j] = __ldcs(work + 2 * (v + j) + 1);
+        }
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (j < nv) {
+            work[2 * (v + j)] = zero;
+            work[2 * (v + j) + 1] = zero;
+            o4[j] = a[j].x;
+            avg_voxel(a[j], b[j], r8[2 * j], r8[2 * j + 1], s12[3 * j], s12[3 * j + 1], s12[3 * j + 2]);
+        }
+    if (nv == kVoxPerThread) {   // v is a multiple of 4: all three addresses are 16-byte aligned
+        __stcs(reinterpret_cast<float4 *>(grid_obj + v), make_float4(o4[0], o4[1], o4[2], o4[3]));
+        __stcs(reinterpret_cast<float4 *>(grid_rot + 2 * v), make_float4(r8[0], r8[1], r8[2], r8[3]));
+        __stcs(reinterpret_cast<float4 *>(grid_rot + 2 * v) + 1, make_float4(r8[4], r8[5], r8[6], r8[7]));
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            __stcs(reinterpret_cast<float4 *>(grid_scale + 3 * v) + k,
+                   make_float4(s12[4 * k], s12[4 * k + 1], s12[4 * k + 2], s12[4 * k + 3]));
     } else {
-        const int cnt = 3 * (int)min((int64_t)kFinalizeThreads, rem);
-        for (int k = threadIdx.x; k < cnt; k += kFinalizeThreads) dst[k] = s_scale[k];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < nv) {
+                grid_obj[v + j] = o4[j];
+                grid_rot[2 * (v + j)] = r8[2 * j];
+                grid_rot[2 * (v + j) + 1] = r8[2 * j + 1];
+                grid_scale[3 * (v + j)] = s12[3 * j];
+                grid_scale[3 * (v + j) + 1] = s12[3 * j + 1];
+                grid_scale[3 * (v + j) + 2] = s12[3 * j + 2];
+            }
     }
 }
 
@@ -404,7 +433,7 @@ extern "C" int cvb200_hv_grid_dims(const float *d_points, int64_t n, float res, 
 }
 
 extern "C" size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]) {
-    if (!dims) return 0;
+    if (!dims || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return 0;
     return (size_t)dims[0] * dims[1] * dims[2] * 8 * sizeof(float);
 }
 
@@ -420,9 +449,11 @@ extern "C" int cvb200_hv_forward(const float *d_points, const float *d_xyz, cons
                 (long long)n, num_rots);
     CVB_REQUIRE(d_grid_obj && d_grid_rot && d_grid_scale && d_work, CVB200_EINVAL, "hv_forward: NULL output/work");
     CVB_REQUIRE(n == 0 || (d_points && d_xyz && d_scale && d_obj), CVB200_EINVAL, "hv_forward: NULL input");
-    CVB_REQUIRE(work_bytes >= cvb200_hv_forward_work_bytes(dims), CVB200_ESCRATCH,
-                "hv_forward: workspace %zu < %zu bytes", work_bytes, cvb200_hv_forward_work_bytes(dims));
-    CVB_REQUIRE((reinterpret_cast<uintptr_t>(d_work) & 31) == 0, CVB200_EINVAL, "hv_forward: workspace must be 32-byte aligned");
+    const size_t need = cvb200_hv_forward_work_bytes(dims);
+    CVB_REQUIRE(work_bytes >= need, CVB200_ESCRATCH, "hv_forward: workspace %zu < %zu bytes", work_bytes, need);
+    CVB_REQUIRE(((reinterpret_cast<uintptr_t>(d_work) | reinterpret_cast<uintptr_t>(d_grid_obj) |
+                  reinterpret_cast<uintptr_t>(d_grid_rot) | reinterpret_cast<uintptr_t>(d_grid_scale)) & 15) == 0,
+                CVB200_EINVAL, "hv_forward: workspace and outputs must be 16-byte aligned");
     const int64_t G = (int64_t)g.X * g.Y * g.Z;
     if (n > 0) {
         const int64_t blocks = ceil_div(n, kPtsPerBlock);
@@ -430,8 +461,8 @@ extern "C" int cvb200_hv_forward(const float *d_points, const float *d_xyz, cons
             d_points, d_xyz, d_scale, d_obj, n, num_rots, g, (float *)d_work);
         CVB_LAUNCH_CHECK("hv_scatter_kernel");
     }
-    hv_finalize_kernel<<<(unsigned)ceil_div(G, kFinalizeThreads), kFinalizeThreads, 0, stream>>>(
-        (float4 *)d_work, G, d_grid_obj, (float2 *)d_grid_rot, d_grid_scale);
+    hv_finalize_kernel<<<(unsigned)ceil_div(G, kFinalizeThreads * kVoxPerThread), kFinalizeThreads, 0, stream>>>(
+        (float4 *)d_work, G, d_grid_obj, d_grid_rot, d_grid_scale);
     CVB_LAUNCH_CHECK("hv_finalize_kernel");
     return 0;
 }

@@ -77,12 +77,13 @@ def grid_dims(points, res):
 
 
 def _workspace(L, dims, device):
+    """Zero-filled ONCE per (device, stream); cvb200_hv_forward leaves it all-zero again
+    (include/cvb200.h contract), so a larger workspace is reused for smaller grids."""
     need = L.cvb200_hv_forward_work_bytes(_lib.i3(dims))
     key = (device.index, torch.cuda.current_stream().cuda_stream)
     w = _work_cache.get(key)
-    if w is None or w.numel() * 4 < need:
-        # zero-filled ONCE; cvb200_hv_forward leaves it zeroed (include/cvb200.h contract)
-        w = torch.zeros((need + 3) // 4, dtype=torch.float32, device=device)
+    if w is None or w.numel() < need:
+        w = torch.zeros(need, dtype=torch.uint8, device=device)
         _work_cache[key] = w
     return w
 
@@ -98,7 +99,7 @@ def forward_host(points, xyz, scale, obj, res, num_rots, corner, dims):
     work = _workspace(L, dims, points.device)
     rc = L.cvb200_hv_forward(_ptr(points), _ptr(xyz), _ptr(scale), _ptr(obj), points.shape[0], float(res),
                              int(num_rots), _lib.f3(corner), _lib.i3(dims), _ptr(grid_obj), _ptr(grid_rot),
-                             _ptr(grid_scale), _ptr(work), work.numel() * 4, _stream_ptr())
+                             _ptr(grid_scale), _ptr(work), work.numel(), _stream_ptr())
     if rc != 0:
         _work_cache.clear()  # the all-zero contract may be broken
     _lib.check(rc, "cvb200_hv_forward")

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 1
+#define CVB200_ABI_VERSION 3
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -50,11 +50,11 @@ size_t cvb200_hv_grid_dims_work_bytes(void);
 int cvb200_hv_grid_dims(const float *d_points, int64_t n, float res, void *d_work,
                         float *h_corner, float *h_maxpt, int32_t *h_dims, void *stream);
 
-/* Bytes of the interleaved accumulation workspace for a grid of X*Y*Z voxels.
+/* Bytes of the device workspace of cvb200_hv_forward for a grid of dims[0..2] voxels:
+ * an interleaved accumulator of 8 floats (one 32-byte sector) per voxel.
  * CONTRACT: the workspace must be all-zero when cvb200_hv_forward is entered and is
- * all-zero again when the call's work completes (the write-out pass re-zeroes it),
- * so a caller zero-fills it once after allocation and may then reuse it forever
- * on the same stream. */
+ * all-zero again when the call's work completes (the write-out pass re-zeroes it), so a caller zero-fills it once after allocation and may
+ * then reuse it forever on the same stream.  16-byte alignment required. */
 size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]);
 
 /* hv_cuda.forward (houghvoting/src/hv_cuda.cpp:30-45 -> hv_cuda_kernel.cu:121-165):
@@ -64,7 +64,8 @@ size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]);
  *   d_points,d_xyz,d_scale [n,3]; d_obj [n]
  *   corner[3], dims[3]     host values (from cvb200_hv_grid_dims or the caller)
  *   d_grid_obj [X,Y,Z], d_grid_rot [X,Y,Z,2], d_grid_scale [X,Y,Z,3]: outputs, every
- *       element is written (no pre-zeroing needed; the reference needs 3 memsets)
+ *       element is written exactly once (no pre-zeroing needed; the reference needs 3
+ *       memsets)
  *   d_work / work_bytes    see cvb200_hv_forward_work_bytes */
 int cvb200_hv_forward(const float *d_points, const float *d_xyz, const float *d_scale, const float *d_obj,
                       int64_t n, float res, int32_t num_rots, const float corner[3], const int32_t dims[3],

@@ -148,9 +148,12 @@ def test_full_size_properties_C5():
     nz = go > 1e-3
     assert gs[nz].min() >= s.min() * (1 - 1e-4) and gs[nz].max() <= s.max() * (1 + 1e-4)
     assert (gr[nz].norm(dim=-1) <= 1 + 1e-4).all()
-    # idempotence: the workspace is left zeroed, a second call reproduces the first
-    go3, _, _ = hv_cuda.forward(p, x, s, o, res_t, rots_t)
-    assert_grid_close(go3.cpu().numpy(), go.cpu().numpy(), what="idempotence")
+    # idempotence: the write-out re-zeroes what the scatter touched, so the cached workspace is all-zero
+    # again and a second / third call reproduces the first
+    for _ in range(2):
+        go3, gr3, gs3 = hv_cuda.forward(p, x, s, o, res_t, rots_t)
+        assert_grid_close(go3.cpu().numpy(), go.cpu().numpy(), what="idempotence obj")
+        assert_grid_close(gs3.cpu().numpy(), gs.cpu().numpy(), what="idempotence scale")
     for w in H._work_cache.values():
         assert not w.any(), "workspace not re-zeroed"
 

@@ -1,0 +1,17 @@
+#!/bin/bash
+# tools/gpu_check.sh TAG [pytest-args] -- runs ON THE GPU BOX (via gpurun): GPU tests, the C2/C5 vote benches,
+# the ncu launch list of the bench and one --set full capture of our kernels; everything lands in gpurun_out/.
+TAG=${1:-x}; shift
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q "$@" 2>&1 | tail -12
+python bench.py --cpu-seconds 3 2>&1 | tail -1 | tee gpurun_out/bench_${TAG}.json | cut -c1-1500
+python bench.py --workload C5 --steps 20 --cpu-seconds 2 2>&1 | tail -1 | tee gpurun_out/bench_${TAG}_c5.json | cut -c1-400
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'hv_|cvb' -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --cpu-seconds 1 > gpurun_out/ncu_b.log 2>&1
+python - <<PY
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/launches_${TAG}.csv")) if len(r)>10]
+h=rows[0]; k=h.index("Kernel Name"); v=h.index("Metric Value")
+for r in rows[-10:]: print(r[k][:60], r[v])
+PY
+ncu --set full --clock-control none --import-source on -k regex:'hv_|cvb' -s 15 -c 5 -o gpurun_out/prof_${TAG} -f python bench.py --steps 3 --warmup 3 --cpu-seconds 1 > gpurun_out/ncu_c.log 2>&1
+ls -la gpurun_out | tail -5
