@@ -30,7 +30,24 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+
+
+class BpParams(ctypes.Structure):
+    """cvb200_bp_params (include/cvb200.h)."""
+    _fields_ = [("thresh_high", ctypes.c_float), ("thresh_low", _i32), ("valid_ratio", ctypes.c_float),
+                ("elimination", _i32), ("elim_hi_inclusive", _i32), ("prob_thresh", ctypes.c_float),
+                ("err_thresh", ctypes.c_float), ("max_boxes", _i32), ("max_iters", _i32), ("max_trace", _i32)]
+
+
+SIGNATURES.update({
+    "cvb200_bp_default_params": (None, [ctypes.POINTER(BpParams)]),
+    "cvb200_bp_work_bytes": (ctypes.c_size_t, [ctypes.POINTER(_i32)]),
+    "cvb200_back_project": (ctypes.c_int, [_f, _f, _f, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_float), ctypes.c_float,
+                                            _f, _f, _f, _vp, _i64, ctypes.POINTER(BpParams), _f, _f, _vp, _vp, _vp, _vp,
+                                            ctypes.c_size_t, _vp]),
+})
+
 _lib = None
 
 

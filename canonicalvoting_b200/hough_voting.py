@@ -4,10 +4,13 @@ reference copy-pastes into every script (HVFunction / HoughVoting, train_joint.p
     vote(points, xyz, scale, obj, res, num_rots)  == hv_cuda.forward with the same arguments
     vote_host(...)                                 fully asynchronous variant: python scalars + known geometry
     HVFunction / HoughVoting                       as in the reference scripts
+    back_project(...)                              the candidate loop + LCC-aware back-projection check
+                                                   (eval_joint.py:195-263) as one device-resident loop
 """
 import torch
 
 from . import hv_cuda
+from .back_project import back_project, back_project_numpy  # noqa: F401
 
 
 def vote(points, xyz, scale, obj, res, num_rots, corners=None):

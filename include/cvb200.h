@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 3
+#define CVB200_ABI_VERSION 4
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -93,6 +93,46 @@ int cvb200_hv_vote_indices(const float *d_points, const float *d_xyz, const floa
  * (hv_cuda_kernel.cu:35-38); d_cos,d_sin [num_rots].  Lets a CPU checker share the
  * exact table. */
 int cvb200_hv_theta_table(int32_t num_rots, float *d_cos, float *d_sin, void *stream);
+
+/* ------------------------------------------------------- candidate loop / back-projection ---- */
+
+/* Thresholds of the candidate loop; cvb200_bp_default_params() fills in the reference's module
+ * globals (eval_joint.py:18-21: thresh_high=60, thresh_low=10, valid_ratio=0.2, elimination=2)
+ * and literals (0.3 / 0.3 at eval_joint.py:245,252). */
+typedef struct cvb200_bp_params {
+    float thresh_high;          /* stop when max(grid_obj) < thresh_high               (:208) */
+    int32_t thresh_low;         /* reject a box with fewer points inside               (:246) */
+    float valid_ratio;          /* reject if confident points < valid_ratio * inside   (:246) */
+    int32_t elimination;        /* half-width of the zeroed neighbourhood              (:211) */
+    int32_t elim_hi_inclusive;  /* 1: [c-e, c+e] (eval_joint.py:211), 0: [c-e, c+e) (eval_separate.py:209) */
+    float prob_thresh;          /* "confident" = prob_pred > prob_thresh               (:245) */
+    float err_thresh;           /* reject if mean(||xyz_pred - lcc|| * prob) > err_thresh (:250-253) */
+    int32_t max_boxes;          /* capacity of the output arrays */
+    int32_t max_iters;          /* safety bound on loop iterations */
+    int32_t max_trace;          /* capacity (iterations) of d_trace, 0 = no trace */
+} cvb200_bp_params;
+
+void cvb200_bp_default_params(cvb200_bp_params *p);
+size_t cvb200_bp_work_bytes(const int32_t dims[3]);
+
+/* The reference's inline `while True:` candidate loop (eval_joint.py:204-263, train_joint.py:364-424)
+ * as one persistent device loop with no host synchronisation: argmax(grid_obj) -> zero the
+ * neighbourhood -> oriented box from grid_rot/grid_scale -> zero the voxels inside it -> LCC-aware
+ * back-projection check over all points -> class vote / score / corners.
+ *   d_grid_obj [X,Y,Z]      in/out: zeroed in place exactly like the script does
+ *   d_grid_rot [X,Y,Z,2], d_grid_scale [X,Y,Z,3]   outputs of cvb200_hv_forward
+ *   corner[3], res          grid origin (= min(points,0), eval_joint.py:201,206) and voxel size
+ *   d_points,d_xyz [n,3]; d_prob [n]; d_class [n] int64 (torch.argmax dtype), class ids in [0,32)
+ *   d_boxes [max_boxes,8,3], d_scores [max_boxes], d_classes [max_boxes] int32
+ *   d_counts [2] int32      out: {number of boxes, loop iterations}
+ *   d_trace [max_trace,4] int32 (may be NULL): per iteration {peak flat index, points inside,
+ *                           confident points inside, accepted} -- verification aid
+ * Asynchronous; read d_counts after synchronising the stream. */
+int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, const float *d_grid_scale,
+                        const int32_t dims[3], const float corner[3], float res, const float *d_points,
+                        const float *d_xyz, const float *d_prob, const int64_t *d_class, int64_t n,
+                        const cvb200_bp_params *params, float *d_boxes, float *d_scores, int32_t *d_classes,
+                        int32_t *d_counts, int32_t *d_trace, void *d_work, size_t work_bytes, void *stream);
 
 #ifdef __cplusplus
 }
