@@ -30,7 +30,7 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class BpParams(ctypes.Structure):
@@ -46,6 +46,16 @@ SIGNATURES.update({
     "cvb200_back_project": (ctypes.c_int, [_f, _f, _f, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_float), ctypes.c_float,
                                             _f, _f, _f, _vp, _i64, ctypes.POINTER(BpParams), _f, _f, _vp, _vp, _vp, _vp,
                                             ctypes.c_size_t, _vp]),
+})
+
+SIGNATURES.update({
+    "cvb200_sc_hash_capacity": (_i64, [_i64]),
+    "cvb200_sc_build_table": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "cvb200_sc_down_flags": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "cvb200_sc_down_finish": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cvb200_sc_kernel_map": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "cvb200_sc_conv_forward": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
+    "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
 })
 
 _lib = None

@@ -1,0 +1,184 @@
+"""SparseTensor and the layer classes of the MinkowskiEngine subset the reference uses:
+MinkowskiConvolution / MinkowskiConvolutionTranspose / MinkowskiBatchNorm / MinkowskiReLU / cat / BasicBlock.
+Class names, constructor arguments and attribute names (`kernel`, `bias`, `bn`, `conv1`, `norm1`, ...)
+follow ME so that utils/minkunet.py and utils/resnet.py of the reference run unchanged and state-dict keys
+match (`conv0p1s1.kernel [125,3,32]`, `block1.0.norm1.bn.weight`, `final.bias [1,64]`).  [ME-recall] marks
+behaviour restated from recollection of ME 0.5.x (the package is not available offline)."""
+import math
+
+import torch
+import torch.nn as nn
+
+from .coords import CoordinateManager
+from .functional import sparse_conv
+
+
+class SparseTensor:
+    """Features [N,C] + integer coordinates [N,4] (batch,x,y,z) sharing a CoordinateManager.
+    `ME.SparseTensor(feats, coords, device='cuda')` (train_joint.py:250): CPU inputs are moved to the device;
+    row order is preserved (callers index `.F` with labels in input order, train_joint.py:256)."""
+
+    def __init__(self, features, coordinates=None, device=None, coordinate_manager=None, tensor_stride=1, **_ignored):
+        if coordinate_manager is None:
+            if coordinates is None:
+                raise ValueError("coordinates or coordinate_manager required")
+            dev = torch.device(device) if device is not None else (features.device if features.is_cuda else torch.device("cuda"))
+            if dev.type != "cuda":
+                raise RuntimeError("canonicalvoting_b200.sparse has no CPU path: pass device='cuda'")
+            coordinates = coordinates.to(device=dev, dtype=torch.int32)
+            features = features.to(dev)
+            coordinate_manager = CoordinateManager(coordinates)
+        self._F = features
+        self.coordinate_manager = coordinate_manager
+        self.tensor_stride = tensor_stride if isinstance(tensor_stride, int) else int(tensor_stride[0])
+
+    @property
+    def F(self):
+        return self._F
+
+    @property
+    def C(self):
+        return self.coordinate_manager.levels[self.tensor_stride].coords
+
+    @property
+    def device(self):
+        return self._F.device
+
+    @property
+    def shape(self):
+        return self._F.shape
+
+    def _like(self, feats, tensor_stride=None):
+        return SparseTensor(feats, coordinate_manager=self.coordinate_manager,
+                            tensor_stride=self.tensor_stride if tensor_stride is None else tensor_stride)
+
+    def __add__(self, other):
+        return self._like(self._F + (other._F if isinstance(other, SparseTensor) else other))
+
+    __iadd__ = __add__
+
+    def __repr__(self):
+        return "SparseTensor(N=%d, C=%d, tensor_stride=%d)" % (self._F.shape[0], self._F.shape[1], self.tensor_stride)
+
+
+def cat(*tensors):
+    """ME.cat (utils/minkunet.py:153-177): channel concatenation of tensors on the same coordinate map."""
+    if len(tensors) == 1 and isinstance(tensors[0], (list, tuple)):
+        tensors = tensors[0]
+    t0 = tensors[0]
+    for t in tensors[1:]:
+        if t.coordinate_manager is not t0.coordinate_manager or t.tensor_stride != t0.tensor_stride:
+            raise ValueError("cat: tensors must share the coordinate map")
+    return t0._like(torch.cat([t.F for t in tensors], 1))
+
+
+class _ConvBase(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, dilation, bias, dimension, transpose):
+        super().__init__()
+        if dimension != 3:
+            raise NotImplementedError("only dimension=3 (the reference uses D=3 everywhere)")
+        if dilation != 1:
+            raise NotImplementedError("dilation != 1 is never used by MinkUNet (utils/minkunet.py:39)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.dilation, self.dimension = kernel_size, stride, dilation, dimension
+        self.is_transpose = transpose
+        self.kernel_volume = kernel_size ** 3
+        shape = (in_channels, out_channels) if self.kernel_volume == 1 else (self.kernel_volume, in_channels, out_channels)
+        self.kernel = nn.Parameter(torch.empty(shape))
+        self.bias = nn.Parameter(torch.empty(1, out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # [ME-recall] MinkowskiConvolutionBase.reset_parameters: uniform(+-1/sqrt(fan)), fan = channels * kernel volume
+        n = (self.out_channels if self.is_transpose else self.in_channels) * self.kernel_volume
+        stdv = 1.0 / math.sqrt(n)
+        with torch.no_grad():
+            self.kernel.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.uniform_(-stdv, stdv)
+
+    def extra_repr(self):
+        return "in=%d, out=%d, kernel_size=%d, stride=%d" % (self.in_channels, self.out_channels, self.kernel_size, self.stride)
+
+
+class MinkowskiConvolution(_ConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False, kernel_generator=None,
+                 dimension=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, dilation, bias, dimension, False)
+
+    def forward(self, x):
+        cm, ts = x.coordinate_manager, x.tensor_stride
+        if self.kernel_size == 1 and self.stride == 1:
+            f = x.F @ self.kernel                      # plain library GEMM (1x1x1 convolution)
+            if self.bias is not None:
+                f = f + self.bias
+            return x._like(f)
+        if self.stride == 1 and self.kernel_size % 2 == 1:
+            nbr = cm.kernel_map(ts, self.kernel_size)
+            return x._like(sparse_conv(x.F, self.kernel, self.bias, nbr, nbr, "same"))
+        if self.stride == 2 and self.kernel_size == 2:
+            d = cm.down(ts)
+            return x._like(sparse_conv(x.F, self.kernel, self.bias, d["children"], d["up_table"], "down"), 2 * ts)
+        raise NotImplementedError("kernel_size=%d stride=%d is not used by the reference" % (self.kernel_size, self.stride))
+
+
+class MinkowskiConvolutionTranspose(_ConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False, kernel_generator=None,
+                 dimension=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, dilation, bias, dimension, True)
+
+    def forward(self, x):
+        cm, ts = x.coordinate_manager, x.tensor_stride
+        if not (self.stride == 2 and self.kernel_size == 2):
+            raise NotImplementedError("only kernel_size=2, stride=2 (utils/minkunet.py:85-106)")
+        fine = ts // 2
+        if fine not in cm._down:
+            raise RuntimeError("transposed convolution onto tensor stride %d: that coordinate map was never created "
+                               "(the decoder re-uses the encoder's maps)" % fine)
+        d = cm._down[fine]
+        return x._like(sparse_conv(x.F, self.kernel, self.bias, d["up_table"], d["children"], "up"), fine)
+
+
+class MinkowskiBatchNorm(nn.Module):
+    """BatchNorm1d over the [N,C] feature matrix of the whole batch [ME-recall]; `.bn` holds the parameters."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
+                                 track_running_stats=track_running_stats)
+
+    def forward(self, x):
+        return x._like(self.bn(x.F))
+
+
+class MinkowskiReLU(nn.Module):
+    def __init__(self, inplace=False):
+        super().__init__()
+        self.inplace = inplace
+
+    def forward(self, x):
+        return x._like(torch.relu(x.F))
+
+
+class BasicBlock(nn.Module):
+    """MinkowskiEngine.modules.resnet_block.BasicBlock [ME-recall]: conv3-norm-relu-conv3-norm (+downsample) -relu."""
+    expansion = 1
+    NORM_TYPE = "BN"
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, bn_momentum=0.1, dimension=-1):
+        super().__init__()
+        self.conv1 = MinkowskiConvolution(inplanes, planes, kernel_size=3, stride=stride, dilation=dilation, dimension=dimension)
+        self.norm1 = MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.conv2 = MinkowskiConvolution(planes, planes, kernel_size=3, stride=1, dilation=dilation, dimension=dimension)
+        self.norm2 = MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.relu = MinkowskiReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        residual = x
+        out = self.relu(self.norm1(self.conv1(x)))
+        out = self.norm2(self.conv2(out))
+        if self.downsample is not None:
+            residual = self.downsample(x)
+        out = out + residual
+        return self.relu(out)

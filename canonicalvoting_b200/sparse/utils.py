@@ -1,0 +1,57 @@
+"""ME.utils subset used by the reference: batched_coordinates (train_joint.py:82, eval_joint.py:64),
+sparse_quantize (utils/dataloader.py:197) and kaiming_normal_ (utils/resnet.py:112).  Host-side helpers
+of the data loader; semantics from recollection of MinkowskiEngine 0.5.x [ME-recall]."""
+import math
+
+import numpy as np
+import torch
+
+
+def batched_coordinates(coords, dtype=torch.int32, device=None):
+    """list of [Ni, 3] arrays / tensors -> int32 [sum Ni, 4] rows (batch index, x, y, z); float inputs are floored."""
+    out = []
+    for b, c in enumerate(coords):
+        c = torch.as_tensor(np.asarray(c) if not isinstance(c, torch.Tensor) else c)
+        if c.is_floating_point():
+            c = torch.floor(c)
+        c = c.to(torch.int64)
+        out.append(torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int64), c], 1))
+    res = torch.cat(out, 0).to(dtype) if out else torch.zeros((0, 4), dtype=dtype)
+    return res.to(device) if device is not None else res
+
+
+def sparse_quantize(coordinates, features=None, labels=None, quantization_size=None, return_index=False,
+                    return_inverse=False, device=None, **_ignored):
+    """floor(coordinates / quantization_size), one representative row per occupied voxel (the first in input
+    order; ME leaves the choice unspecified).  Returns what ME returns for the argument combination used by the
+    reference: (unique_coords[, features][, labels][, index][, inverse])."""
+    c = np.asarray(coordinates.cpu() if isinstance(coordinates, torch.Tensor) else coordinates)
+    if quantization_size is not None:
+        c = np.floor(c / quantization_size)
+    c = c.astype(np.int64)
+    _, index, inverse = np.unique(c, axis=0, return_index=True, return_inverse=True)
+    order = np.sort(index)                      # keep input order among the representatives
+    remap = np.empty(len(index), np.int64)
+    remap[np.argsort(index)] = np.arange(len(index))
+    outs = [torch.from_numpy(c[order].astype(np.int32))]
+    if features is not None:
+        outs.append(features[order])
+    if labels is not None:
+        outs.append(labels[order])
+    if return_index:
+        outs.append(torch.from_numpy(order))
+    if return_inverse:
+        outs.append(torch.from_numpy(remap[inverse.reshape(-1)]))
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
+    """Kaiming normal for a sparse-convolution kernel [K^D, Cin, Cout] (fan = channels * kernel volume)."""
+    if tensor.dim() == 3:
+        kv, cin, cout = tensor.shape
+    else:
+        kv, (cin, cout) = 1, tensor.shape
+    fan = cin * kv if mode == "fan_in" else cout * kv
+    std = torch.nn.init.calculate_gain(nonlinearity, a) / math.sqrt(fan)
+    with torch.no_grad():
+        return tensor.normal_(0, std)

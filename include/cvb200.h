@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 4
+#define CVB200_ABI_VERSION 5
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -133,6 +133,49 @@ int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, const float 
                         const float *d_xyz, const float *d_prob, const int64_t *d_class, int64_t n,
                         const cvb200_bp_params *params, float *d_boxes, float *d_scores, int32_t *d_classes,
                         int32_t *d_counts, int32_t *d_trace, void *d_work, size_t work_bytes, void *stream);
+
+/* ------------------------------------------------- sparse-voxel U-Net: coordinates + convolution ---- */
+/* These replace what the reference gets from the external MinkowskiEngine package (v0.5.3, README.md:53):
+ * ME.SparseTensor's coordinate manager (train_joint.py:250, eval_joint.py:169) and the kernels behind
+ * ME.MinkowskiConvolution / MinkowskiConvolutionTranspose (utils/minkunet.py:53-114, utils/resnet.py:128).
+ * Coordinates are int32 rows (batch, x, y, z) as produced by ME.utils.batched_coordinates
+ * (train_joint.py:82); batch in [0,65535], x/y/z in [-32768,32767].  Kernel offset k of a K^3 kernel is
+ * k = ix + K*(iy + K*iz) (x fastest; ME's ordering from recollection, unpinned -- see DESIGN.md). */
+
+/* slots of the open-addressing hash table for n rows (a power of two >= 2n) */
+int64_t cvb200_sc_hash_capacity(int64_t n);
+
+/* (re)build the table: d_keys [capacity] uint64, d_vals [capacity] int32; value = row index */
+int cvb200_sc_build_table(const int32_t *d_coords, int64_t n, void *d_keys, int32_t *d_vals, int64_t capacity, void *stream);
+
+/* stride-2 down-sampling, step 1: build the table of COARSE coordinates floor(c / new_stride) * new_stride
+ * and flag the first fine child of every coarse voxel (d_flag [n] int32, 0/1).  The caller turns the
+ * flags into an exclusive prefix sum (coarse rows are numbered by their first child: deterministic). */
+int cvb200_sc_down_flags(const int32_t *d_coords, int64_t n, int32_t new_stride, void *d_keys, int32_t *d_vals,
+                         int64_t capacity, int32_t *d_flag, void *stream);
+
+/* step 2: coarse coordinate rows [n_coarse,4], per fine voxel its parent row and kernel offset (0..7),
+ * the children table [n_coarse,8] (neighbour table of the stride-2 2^3 convolution) and the parent table
+ * [n,8] (neighbour table of the transposed 2^3 convolution: -1 except column koff = parent). */
+int cvb200_sc_down_finish(const int32_t *d_coords, int64_t n, int32_t new_stride, void *d_keys, int32_t *d_vals,
+                          int64_t capacity, const int32_t *d_flag, const int32_t *d_excl_scan, int64_t n_coarse,
+                          int32_t *d_out_coords, int32_t *d_parent, int32_t *d_koff, int32_t *d_children,
+                          int32_t *d_up_table, void *stream);
+
+/* neighbour table of a stride-1 convolution with odd kernel size: d_nbr [n_out, ksize^3] =
+ * row of (coord + (i - ksize/2) * step) in the table, or -1; step = tensor stride of the level */
+int cvb200_sc_kernel_map(const int32_t *d_out_coords, int64_t n_out, const void *d_keys, const int32_t *d_vals,
+                         int64_t capacity, int32_t ksize, int32_t step, int32_t *d_nbr, void *stream);
+
+/* out[o,:] = sum_k in[nbr[o,k],:] @ W[k] (+ bias);  d_w [k3,cin,cout], d_nbr [n_out,k3], d_bias [cout] or NULL.
+ * fp32 CUDA-core path (exact fp32 accumulation). */
+int cvb200_sc_conv_forward(const float *d_in, int32_t cin, const float *d_w, int32_t cout, const int32_t *d_nbr,
+                           int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
+
+/* dW[k] [ca,cb] = sum_r A[ia(r,k),:]^T (x) B[ib(r,k),:] over the table rows r;
+ * table_on_b = 0: ia = table[r,k], ib = r;  table_on_b = 1: ia = r, ib = table[r,k].  d_dw is overwritten. */
+int cvb200_sc_conv_wgrad(const float *d_a, int32_t ca, const float *d_b, int32_t cb, const int32_t *d_table,
+                         int64_t n_rows, int32_t k3, int32_t table_on_b, float *d_dw, void *stream);
 
 #ifdef __cplusplus
 }

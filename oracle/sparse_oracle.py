@@ -1,0 +1,140 @@
+"""oracle/sparse_oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+Slow, obviously-correct restatement of the sparse-convolution semantics the reference obtains from the
+external MinkowskiEngine package (v0.5.3, README.md:53; call sites utils/minkunet.py:53-114).  ME is not
+installable offline and the reference holds no test that pins any ME result, so this oracle is **parity
+unpinned** against ME itself; it is pinned instead against DENSE convolutions (torch.nn.functional.conv3d /
+conv_transpose3d on a densified scene, tests/test_oracle_sparse.py) for every (kernel, stride) variant the
+U-Net uses.  Pure torch on CPU: python dict coordinate maps + index_add_.
+
+Conventions restated from recollection of ME 0.5.x [ME-recall]:
+  * kernel [K^3, Cin, Cout]; offset index k = ix + K*(iy + K*iz) (x fastest), centred for odd K,
+    {0,1}^3 * tensor_stride for the stride-2 2^3 kernel;
+  * stride-2 convolution: output coordinates floor(c / (2 ts)) * 2 ts, new tensor stride 2 ts;
+  * transposed stride-2 convolution: output on the cached finer coordinate map, out[fine] = in[parent] @ W[k]
+    with k the offset of the fine voxel inside its parent.
+"""
+import numpy as np
+import torch
+
+
+def _key(c):
+    return tuple(int(v) for v in c)
+
+
+def coarse_coords(coords, new_stride):
+    """unique floor(c / new_stride) * new_stride in order of first appearance; returns (coarse [M,4], parent [N], koff [N])."""
+    c = coords.clone().long()
+    half = new_stride // 2
+    par = c.clone()
+    par[:, 1:] = torch.div(c[:, 1:], new_stride, rounding_mode="floor") * new_stride
+    index, rows, parent = {}, [], []
+    for r in par.tolist():
+        k = tuple(r)
+        if k not in index:
+            index[k] = len(rows)
+            rows.append(r)
+        parent.append(index[k])
+    off = (c[:, 1:] - par[:, 1:]) // half
+    koff = off[:, 0] + 2 * (off[:, 1] + 2 * off[:, 2])
+    return torch.tensor(rows, dtype=torch.int32), torch.tensor(parent), koff
+
+
+def conv_same(coords, feats, kernel, ksize, tensor_stride=1, bias=None):
+    """stride-1 K^3 convolution (K odd) on the coordinate set `coords` [N,4]."""
+    index = {_key(c): i for i, c in enumerate(coords.tolist())}
+    n, cout = feats.shape[0], kernel.shape[-1]
+    out = torch.zeros((n, cout), dtype=feats.dtype)
+    h = ksize // 2
+    w = kernel.reshape(ksize ** 3, -1, cout)
+    for k in range(ksize ** 3):
+        ix, iy, iz = k % ksize, (k // ksize) % ksize, k // (ksize * ksize)
+        d = ((ix - h) * tensor_stride, (iy - h) * tensor_stride, (iz - h) * tensor_stride)
+        src, dst = [], []
+        for o, c in enumerate(coords.tolist()):
+            j = index.get((c[0], c[1] + d[0], c[2] + d[1], c[3] + d[2]))
+            if j is not None:
+                src.append(j); dst.append(o)
+        if src:
+            out.index_add_(0, torch.tensor(dst), feats[torch.tensor(src)] @ w[k])
+    return out + (bias if bias is not None else 0)
+
+
+def conv_down(coords, feats, kernel, tensor_stride=1, bias=None):
+    """stride-2 2^3 convolution: returns (coarse coords, features)."""
+    coarse, parent, koff = coarse_coords(coords, 2 * tensor_stride)
+    out = torch.zeros((coarse.shape[0], kernel.shape[-1]), dtype=feats.dtype)
+    for k in range(8):
+        m = koff == k
+        if m.any():
+            out.index_add_(0, parent[m], feats[m] @ kernel[k])
+    return coarse, out + (bias if bias is not None else 0)
+
+
+def conv_up(fine_coords, coarse_feats, kernel, tensor_stride=2, bias=None):
+    """transposed stride-2 2^3 convolution from the coarse level (tensor stride `tensor_stride`) onto `fine_coords`."""
+    _, parent, koff = coarse_coords(fine_coords, tensor_stride)
+    out = torch.zeros((fine_coords.shape[0], kernel.shape[-1]), dtype=coarse_feats.dtype)
+    for k in range(8):
+        m = koff == k
+        if m.any():
+            out[m] = coarse_feats[parent[m]] @ kernel[k]
+    return out + (bias if bias is not None else 0)
+
+
+class OracleNet:
+    """Forward pass of a canonicalvoting_b200.minkunet model on CPU through the functions above, reading the
+    parameters from the model's state dict (BatchNorm in the model's train/eval mode)."""
+
+    def __init__(self, model):
+        self.m = model
+
+    def _bn(self, mod, f):
+        bn = mod.bn
+        return torch.nn.functional.batch_norm(f, bn.running_mean.cpu().clone(), bn.running_var.cpu().clone(), bn.weight.detach().cpu(),
+                                              bn.bias.detach().cpu(), bn.training, bn.momentum, bn.eps)
+
+    def _conv(self, mod, coords_by_ts, ts, f):
+        w = mod.kernel.detach().cpu()
+        b = mod.bias.detach().cpu() if mod.bias is not None else None
+        if mod.kernel_size == 1:
+            return ts, f @ w + (b if b is not None else 0)
+        if mod.is_transpose:
+            return ts // 2, conv_up(coords_by_ts[ts // 2], f, w, ts, b)
+        if mod.stride == 2:
+            coarse, out = conv_down(coords_by_ts[ts], f, w, ts, b)
+            coords_by_ts[2 * ts] = coarse
+            return 2 * ts, out
+        return ts, conv_same(coords_by_ts[ts], f, w, mod.kernel_size, ts, b)
+
+    def _block(self, blk, C, ts, f):
+        r = f
+        _, o = self._conv(blk.conv1, C, ts, f)
+        o = torch.relu(self._bn(blk.norm1, o))
+        _, o = self._conv(blk.conv2, C, ts, o)
+        o = self._bn(blk.norm2, o)
+        if blk.downsample is not None:
+            _, r = self._conv(blk.downsample[0], C, ts, f)
+            r = self._bn(blk.downsample[1], r)
+        return torch.relu(o + r)
+
+    def forward(self, coords, feats):
+        from canonicalvoting_b200.minkunet import _DECODER, _ENCODER
+        m, C = self.m, {1: coords.cpu()}
+        ts, f = self._conv(m.conv0p1s1, C, 1, feats.cpu())
+        f = torch.relu(self._bn(m.bn0, f))
+        skips = [f]
+        for conv, bn, block in _ENCODER:
+            ts, f = self._conv(getattr(m, conv), C, ts, f)
+            f = torch.relu(self._bn(getattr(m, bn), f))
+            for blk in getattr(m, block):
+                f = self._block(blk, C, ts, f)
+            skips.append(f)
+        skips.pop()
+        for conv, bn, block in _DECODER:
+            ts, f = self._conv(getattr(m, conv), C, ts, f)
+            f = torch.relu(self._bn(getattr(m, bn), f))
+            f = torch.cat([f, skips.pop()], 1)
+            for blk in getattr(m, block):
+                f = self._block(blk, C, ts, f)
+        return self._conv(m.final, C, ts, f)[1]

@@ -1,0 +1,116 @@
+"""CPU tests that pin the sparse-convolution oracle (oracle/sparse_oracle.py) against DENSE convolutions
+(torch.nn.functional.conv3d / conv_transpose3d on the densified scene) for every (kernel, stride) variant of
+MinkUNet34C, plus the host-side ME.utils helpers and the model's structure.  ME itself is unavailable
+offline (parity unpinned); dense equivalence is what pins the semantics."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sparse_oracle as SO
+
+
+def _scene(n=60, G=8, batch=2, cin=3, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for b in range(batch):
+        lin = torch.randperm(G ** 3, generator=g)[:n]
+        rows.append(torch.stack([torch.full_like(lin, b), lin // (G * G), (lin // G) % G, lin % G], 1))
+    coords = torch.cat(rows).int()
+    feats = torch.randn(coords.shape[0], cin, generator=g, dtype=torch.float64)
+    return coords, feats, G, batch
+
+
+def _dense(coords, feats, G, batch):
+    d = torch.zeros(batch, feats.shape[1], G, G, G, dtype=feats.dtype)
+    c = coords.long()
+    d[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]] = feats
+    return d
+
+
+def _w_dense(kernel, K):
+    # kernel [K^3, Cin, Cout], k = ix + K*(iy + K*iz)  ->  conv3d weight [Cout, Cin, kx, ky, kz] (spatial dims x,y,z)
+    cin, cout = kernel.shape[1], kernel.shape[2]
+    return kernel.reshape(K, K, K, cin, cout).permute(4, 3, 2, 1, 0).contiguous()   # [iz,iy,ix,..] -> [.., ix,iy,iz]
+
+
+@pytest.mark.parametrize("K", [3, 5])
+def test_same_conv_equals_dense_conv3d(K):
+    coords, feats, G, batch = _scene()
+    g = torch.Generator().manual_seed(1)
+    kernel = torch.randn(K ** 3, 3, 4, generator=g, dtype=torch.float64)
+    out = SO.conv_same(coords, feats, kernel, K)
+    dense = F.conv3d(_dense(coords, feats, G, batch), _w_dense(kernel, K), padding=K // 2)
+    c = coords.long()
+    torch.testing.assert_close(out, dense[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]])
+
+
+def test_same_conv_at_tensor_stride_2_is_a_dilated_dense_conv():
+    coords, feats, G, batch = _scene(n=40, G=8)
+    coords = coords.clone(); coords[:, 1:] *= 2            # a stride-2 coordinate set
+    kernel = torch.randn(27, 3, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    out = SO.conv_same(coords, feats, kernel, 3, tensor_stride=2)
+    dense = F.conv3d(_dense(coords, feats, 2 * G, batch), _w_dense(kernel, 3), padding=2, dilation=2)
+    c = coords.long()
+    torch.testing.assert_close(out, dense[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]])
+
+
+def test_down_conv_equals_dense_stride2_conv():
+    coords, feats, G, batch = _scene(n=80, G=8)
+    kernel = torch.randn(8, 3, 6, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    coarse, out = SO.conv_down(coords, feats, kernel, tensor_stride=1)
+    dense = F.conv3d(_dense(coords, feats, G, batch), _w_dense(kernel, 2), stride=2)
+    c = coarse.long()
+    assert (c[:, 1:] % 2 == 0).all()
+    torch.testing.assert_close(out, dense[c[:, 0], :, c[:, 1] // 2, c[:, 2] // 2, c[:, 3] // 2])
+    # every occupied coarse cell is present exactly once
+    occ = (F.max_pool3d(_dense(coords, torch.ones(len(coords), 1, dtype=torch.float64), G, batch), 2) > 0).sum()
+    assert len(coarse) == int(occ) == len({tuple(r) for r in coarse.tolist()})
+
+
+def test_up_conv_equals_dense_conv_transpose():
+    coords, feats, G, batch = _scene(n=80, G=8)
+    coarse, parent, koff = SO.coarse_coords(coords, 2)
+    cf = torch.randn(len(coarse), 4, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    kernel = torch.randn(8, 4, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    out = SO.conv_up(coords, cf, kernel, tensor_stride=2)
+    cc = coarse.clone(); cc[:, 1:] //= 2
+    dense_in = _dense(cc, cf, G // 2, batch)
+    # conv_transpose3d weight [Cin, Cout, kx, ky, kz]
+    wt = kernel.reshape(2, 2, 2, 4, 3).permute(3, 4, 2, 1, 0).contiguous()
+    dense = F.conv_transpose3d(dense_in, wt, stride=2)
+    c = coords.long()
+    torch.testing.assert_close(out, dense[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]])
+
+
+def test_negative_coordinates_floor():
+    coords = torch.tensor([[0, -1, -2, -3], [0, -4, 0, 1], [0, 3, 2, 1]], dtype=torch.int32)
+    coarse, parent, koff = SO.coarse_coords(coords, 2)
+    assert coarse.tolist() == [[0, -2, -2, -4], [0, -4, 0, 0], [0, 2, 2, 0]]
+    assert koff.tolist() == [1 + 2 * (0 + 2 * 1), 0 + 2 * (0 + 2 * 1), 1 + 2 * (0 + 2 * 1)]
+
+
+def test_me_utils_helpers():
+    import MinkowskiEngine as ME
+    bc = ME.utils.batched_coordinates([np.array([[0.2, 1.7, -0.5]]), torch.tensor([[3, 4, 5], [6, 7, 8]])])
+    assert bc.dtype == torch.int32 and bc.tolist() == [[0, 0, 1, -1], [1, 3, 4, 5], [1, 6, 7, 8]]
+    pts = np.array([[0.01, 0.02, 0.0], [0.05, 0.0, 0.0], [0.02, 0.01, 0.02], [0.31, 0.0, 0.0]])
+    idx = ME.utils.sparse_quantize(pts, quantization_size=0.03, return_index=True)[1]
+    assert sorted(idx.tolist()) == [0, 1, 3]       # rows 0 and 2 share voxel (0,0,0)
+    k = torch.empty(27, 16, 32)
+    ME.utils.kaiming_normal_(k, mode="fan_out", nonlinearity="relu")
+    assert abs(float(k.std()) - (2.0 / (32 * 27)) ** 0.5) < 0.01
+
+
+def test_minkunet34c_structure_matches_the_reference_model():
+    from canonicalvoting_b200.minkunet import MinkUNet34C
+    m = MinkUNet34C(3, 64)
+    sd = m.state_dict()
+    assert sum(p.numel() for p in m.parameters()) == 37_860_320 and len(list(m.parameters())) == 188
+    assert tuple(sd["conv0p1s1.kernel"].shape) == (125, 3, 32)
+    assert tuple(sd["block5.0.conv1.kernel"].shape) == (27, 384, 256)
+    assert tuple(sd["final.kernel"].shape) == (96, 64) and tuple(sd["final.bias"].shape) == (1, 64)
+    assert "block1.0.norm1.bn.running_mean" in sd and "block2.0.downsample.0.kernel" in sd
+    n_conv = sum(1 for k in sd if k.endswith("kernel"))
+    n_bn = sum(1 for k in sd if k.endswith("bn.weight"))
+    assert (n_conv, n_bn) == (63, 62)

@@ -1,0 +1,144 @@
+"""GPU parity tests of the sparse-voxel stack (csrc/sparse_coords.cu, csrc/sparse_conv*.cu through the C ABI and
+the MinkowskiEngine-compatible modules) against oracle/sparse_oracle.py (which tests/test_oracle_sparse.py pins
+to dense conv3d).  fp32 CUDA-core path: 1e-5 relative; coordinate maps: exact; gradients: against torch
+autograd through the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sparse_oracle as SO
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(n=3000, G=24, batch=2, cin=3, seed=0, negative=False):
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for b in range(batch):
+        lin = torch.randperm(G ** 3, generator=g)[:n]
+        rows.append(torch.stack([torch.full_like(lin, b), lin // (G * G), (lin // G) % G, lin % G], 1))
+    coords = torch.cat(rows).int()
+    if negative:
+        coords[:, 1:] -= G // 2
+    feats = torch.randn(coords.shape[0], cin, generator=g)
+    return coords, feats
+
+
+def _close(a, b, rtol=1e-5, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    scale = max(1.0, float(b.abs().max()))
+    err = float((a - b).abs().max())
+    assert a.shape == b.shape and err <= rtol * scale, "%s: max abs err %.3e (scale %.3e)" % (what, err, scale)
+
+
+@pytest.mark.parametrize("negative", [False, True])
+def test_coordinate_maps_match_oracle(negative):
+    import MinkowskiEngine as ME
+    coords, feats = _scene(negative=negative)
+    st = ME.SparseTensor(feats, coords, device="cuda")
+    cm = st.coordinate_manager
+    d = cm.down(1)
+    coarse, parent, koff = SO.coarse_coords(coords, 2)
+    assert torch.equal(cm.levels[2].coords.cpu(), coarse)          # numbered by first child: deterministic
+    assert torch.equal(d["parent"].cpu().long(), parent) and torch.equal(d["koff"].cpu().long(), koff)
+    ch = d["children"].cpu()
+    for i in range(0, len(coords), 97):
+        assert ch[parent[i], koff[i]] == i
+    assert int((ch >= 0).sum()) == len(coords)
+    nbr = cm.kernel_map(1, 3).cpu()
+    index = {tuple(c): i for i, c in enumerate(coords.tolist())}
+    for o in range(0, len(coords), 211):
+        c = coords[o].tolist()
+        for k in range(27):
+            ix, iy, iz = k % 3 - 1, (k // 3) % 3 - 1, k // 9 - 1
+            assert nbr[o, k] == index.get((c[0], c[1] + ix, c[2] + iy, c[3] + iz), -1)
+    # second level: stride-4 coordinates from the stride-2 level, kernel map with step 2
+    cm.down(2)
+    c4, _, _ = SO.coarse_coords(coarse, 4)
+    assert torch.equal(cm.levels[4].coords.cpu(), c4)
+    nbr2 = cm.kernel_map(2, 3).cpu()
+    index2 = {tuple(c): i for i, c in enumerate(coarse.tolist())}
+    for o in range(0, len(coarse), 53):
+        c = coarse[o].tolist()
+        for k in (0, 5, 13, 22, 26):
+            ix, iy, iz = k % 3 - 1, (k // 3) % 3 - 1, k // 9 - 1
+            assert nbr2[o, k] == index2.get((c[0], c[1] + 2 * ix, c[2] + 2 * iy, c[3] + 2 * iz), -1)
+
+
+@pytest.mark.parametrize("K,cin,cout", [(3, 3, 32), (5, 3, 32), (3, 32, 64), (3, 96, 96), (3, 40, 24)])
+def test_conv_same_forward_backward(K, cin, cout):
+    import MinkowskiEngine as ME
+    coords, feats = _scene(n=2000, G=20, cin=cin, seed=K + cin)
+    conv = ME.MinkowskiConvolution(cin, cout, kernel_size=K, bias=True, dimension=3).cuda()
+    x = feats.cuda().requires_grad_(True)
+    y = conv(ME.SparseTensor(x, coords, device="cuda")).F
+    xo = feats.clone().double().requires_grad_(True)
+    wo = conv.kernel.detach().cpu().double().requires_grad_(True)
+    bo = conv.bias.detach().cpu().double().requires_grad_(True)
+    yo = SO.conv_same(coords, xo, wo, K, 1, bo)
+    _close(y, yo, what="forward")
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
+    y.backward(gy.cuda())
+    yo.backward(gy.double())
+    _close(x.grad, xo.grad, what="dX")
+    _close(conv.kernel.grad, wo.grad, rtol=2e-5, what="dW")
+    _close(conv.bias.grad, bo.grad, rtol=2e-5, what="dbias")
+
+
+def test_conv_down_up_forward_backward():
+    import MinkowskiEngine as ME
+    coords, feats = _scene(n=2500, G=22, cin=32, seed=9, negative=True)
+    down = ME.MinkowskiConvolution(32, 48, kernel_size=2, stride=2, dimension=3).cuda()
+    up = ME.MinkowskiConvolutionTranspose(48, 24, kernel_size=2, stride=2, dimension=3).cuda()
+    x = feats.cuda().requires_grad_(True)
+    s0 = ME.SparseTensor(x, coords, device="cuda")
+    s1 = down(s0)
+    s2 = up(s1)
+    assert s1.tensor_stride == 2 and s2.tensor_stride == 1 and s2.F.shape == (len(coords), 24)
+    xo = feats.clone().double().requires_grad_(True)
+    wd = down.kernel.detach().cpu().double().requires_grad_(True)
+    wu = up.kernel.detach().cpu().double().requires_grad_(True)
+    coarse, f1 = SO.conv_down(coords, xo, wd, 1)
+    f2 = SO.conv_up(coords, f1, wu, 2)
+    assert torch.equal(s1.C.cpu(), coarse)
+    _close(s1.F, f1, what="down forward")
+    _close(s2.F, f2, what="up forward")
+    gy = torch.randn(f2.shape, generator=torch.Generator().manual_seed(2))
+    s2.F.backward(gy.cuda())
+    f2.backward(gy.double())
+    _close(x.grad, xo.grad, what="dX")
+    _close(down.kernel.grad, wd.grad, rtol=2e-5, what="dW down")
+    _close(up.kernel.grad, wu.grad, rtol=2e-5, what="dW up")
+
+
+def test_minkunet_forward_matches_oracle_net_and_backward_runs():
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200.minkunet import MinkUNet14A
+    torch.manual_seed(0)
+    coords, feats = _scene(n=1500, G=40, batch=2, cin=3, seed=3)
+    model = MinkUNet14A(3, 20).cuda().eval()
+    with torch.no_grad():
+        for m in model.modules():                       # non-trivial BN statistics
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+        y = model(ME.SparseTensor(feats, coords, device="cuda")).F
+    yo = SO.OracleNet(model).forward(coords, feats)
+    assert y.shape == (len(coords), 20)
+    _close(y, yo, rtol=2e-4, what="MinkUNet14A eval forward")
+    model.train()
+    out = model(ME.SparseTensor(feats, coords, device="cuda")).F
+    out.square().mean().backward()
+    for n_, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n_
+
+
+def test_reference_row_order_and_errors():
+    import MinkowskiEngine as ME
+    coords, feats = _scene(n=500, G=12, batch=1)
+    st = ME.SparseTensor(feats, coords, device="cuda")
+    assert torch.equal(st.C.cpu(), coords) and torch.equal(st.F.cpu(), feats)      # input order preserved
+    up = ME.MinkowskiConvolutionTranspose(3, 4, kernel_size=2, stride=2, dimension=3).cuda()
+    with pytest.raises(RuntimeError, match="never created"):
+        up(ME.SparseTensor(feats, coordinate_manager=st.coordinate_manager, tensor_stride=2))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ME.SparseTensor(feats, coords, device="cpu")
