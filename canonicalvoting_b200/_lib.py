@@ -30,7 +30,7 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class BpParams(ctypes.Structure):
@@ -55,6 +55,7 @@ SIGNATURES.update({
     "cvb200_sc_down_finish": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvb200_sc_kernel_map": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "cvb200_sc_conv_forward": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
+    "cvb200_sc_conv_forward_tc": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
 })
 

@@ -1,0 +1,259 @@
+// canonicalvoting_b200/csrc/sparse_conv_tc.cu -- tensor-core (tcgen05 / TMEM) forward of the sparse convolution.
+//
+//     out[o, :] = sum_k  in[nbr[o, k], :] @ W[k]
+// as an output-stationary implicit GEMM on the 5th-generation tensor cores of sm_100a:
+//   * one CTA owns a tile of 128 output rows; its accumulator (128 x Cout fp32) lives in TENSOR MEMORY for the
+//     whole walk over the K^3 kernel offsets and is read back exactly once (tcgen05.ld) by the epilogue;
+//   * per (offset, 32-channel block) the CTA gathers the neighbour rows named by the neighbour table straight
+//     from the feature matrix into a 128B-swizzled K-major shared-memory tile with 16-byte cp.async copies
+//     (rows without a neighbour are zero-filled by a zero-length copy, so only existing pairs cost bandwidth)
+//     and stages the matching 32 x Cout weight block next to it; a 3-4 stage ring overlaps the gathers with
+//     the MMAs;
+//   * ONE elected thread issues tcgen05.mma.kind::tf32 (M=128, N=Cout, K=8; fp32 features and weights are
+//     consumed as TF32, accumulation is fp32) and tcgen05.commit releases each stage through an mbarrier;
+//   * offsets for which no row of the tile has a neighbour are skipped.
+// Weights arrive pre-transposed as Wt[k][cout][cin] (K-major B operand).  Requirements: cin % 32 == 0,
+// cout % 16 == 0, 16 <= cout <= 256, K^3 <= 32.  Everything else (cin = 3 stem, gradients) uses the fp32
+// CUDA-core path in sparse_conv.cu.
+#include "common.cuh"
+
+namespace cvb200 {
+
+constexpr int kTcM = 128;          // output rows per CTA = UMMA M
+constexpr int kTcKB = 32;          // channels per k-block = 128 bytes of tf32 = one swizzle-128B row
+constexpr int kTcThreads = 256;
+constexpr int kTcMaxK3 = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination without reading
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);        // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: next 8-row group            [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)                      [46,48)
+    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B                         [61,64)
+    return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcSmemHeader {
+    unsigned long long empty_bar[4];
+    unsigned int tmem_base;
+    int n_act;
+    int act[kTcMaxK3];
+    int any[kTcMaxK3];
+};
+
+// dynamic smem: [header 1 KiB][nbr tile: K3 x 128 ints, padded to 1 KiB][stages x (A tile 16 KiB | B tile N x 128 B)]
+template <int kStages>
+__global__ void __launch_bounds__(kTcThreads)
+sc_conv_tc_kernel(const float *__restrict__ in, int cin, const float *__restrict__ wt, int cout, const int *__restrict__ nbr,
+                  int n_out, int k3, const float *__restrict__ bias, float *__restrict__ out, int tmem_cols) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    TcSmemHeader &H = *reinterpret_cast<TcSmemHeader *>(smem);
+    int *s_nbr = reinterpret_cast<int *>(smem + 1024);
+    const int nbr_bytes = ((k3 * kTcM * 4 + 1023) / 1024) * 1024;
+    unsigned char *stage0 = smem + 1024 + nbr_bytes;
+    const int a_bytes = kTcM * 128, b_bytes = cout * 128, stage_bytes = a_bytes + b_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * kTcM;
+
+    // ---- prologue: neighbour tile, list of active offsets, barriers, tensor memory
+    if (tid < kTcMaxK3) H.any[tid] = 0;
+    __syncthreads();
+    for (int e = tid; e < k3 * kTcM; e += kTcThreads) {
+        const int r = e / k3, k = e - r * k3;   // consecutive threads read consecutive table entries
+        const int v = row0 + r < n_out ? __ldg(nbr + (size_t)(row0 + r) * k3 + k) : -1;
+        s_nbr[k * kTcM + r] = v;
+        if (v >= 0) H.any[k] = 1;               // benign race
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&H.empty_bar[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&H.tmem_base)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int k = 0; k < k3; k++)
+            if (H.any[k]) H.act[n++] = k;
+        H.n_act = n;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = H.tmem_base;
+    const int cblocks = cin / kTcKB;
+    const int total = H.n_act * cblocks;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = cout, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cout >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+    auto issue_loads = [&](int blk) {
+        const int k = H.act[blk / cblocks], c0 = (blk % cblocks) * kTcKB;
+        unsigned char *st = stage0 + (size_t)(blk % kStages) * stage_bytes;
+        const uint32_t a_s = smem_u32(st), b_s = a_s + a_bytes;
+        const int *idx = s_nbr + k * kTcM;
+        // A: 128 rows x 8 chunks of 16 B; 8 consecutive threads copy one 128-byte row (coalesced, conflict-free)
+        for (int e = tid; e < kTcM * 8; e += kTcThreads) {
+            const int r = e >> 3, c = e & 7;
+            const int src_row = idx[r];
+            const float *src = in + (size_t)(src_row >= 0 ? src_row : 0) * cin + c0 + c * 4;
+            cp_async16(a_s + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src, src_row >= 0 ? 16u : 0u);
+        }
+        // B: cout rows (output channels) x 8 chunks: Wt[k][n][c0 .. c0+32)
+        const float *wk = wt + (size_t)k * cout * cin + c0;
+        for (int e = tid; e < cout * 8; e += kTcThreads) {
+            const int r = e >> 3, c = e & 7;
+            cp_async16(b_s + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), wk + (size_t)r * cin + c * 4, 16u);
+        }
+    };
+
+    // ---- main loop: kStages-deep ring of (gathered A tile, weight tile); one thread issues the MMAs
+    for (int b = 0; b < kStages - 1; b++) {
+        if (b < total) issue_loads(b);
+        cp_async_commit();
+    }
+    for (int it = 0; it < total; it++) {
+        const int pre = it + kStages - 1;
+        if (pre < total) {
+            if (it >= 1) mbar_wait(smem_u32(&H.empty_bar[(it - 1) % kStages]), (uint32_t)(((it - 1) / kStages) & 1));
+            issue_loads(pre);
+        }
+        cp_async_commit();
+        cp_async_wait<kStages - 1>();                                 // block `it` has landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_s = smem_u32(stage0 + (size_t)(it % kStages) * stage_bytes), b_s = a_s + a_bytes;
+            const uint64_t a_desc = umma_desc_k_sw128(a_s), b_desc = umma_desc_k_sw128(b_s);
+#pragma unroll
+            for (int kk = 0; kk < kTcKB / 8; kk++)   // UMMA K = 8 tf32 = 32 bytes: advance the start address inside the swizzle row
+                umma_tf32(tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(smem_u32(&H.empty_bar[it % kStages]));   // arrives when these MMAs (and all before) have completed
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: TMEM -> registers -> (+bias) -> global, each thread one output row, 16 columns at a time
+    if (total > 0) {
+        mbar_wait(smem_u32(&H.empty_bar[(total - 1) % kStages]), (uint32_t)(((total - 1) / kStages) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    {
+        const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter of this warp, column half
+        const int r = row0 + q * 32 + lane;
+        const int ncol16 = cout / 16;
+        for (int cb = half; cb < ncol16; cb += 2) {
+            uint32_t v[16];
+            if (total > 0) {
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = 0u;
+            }
+            if (r < n_out) {
+                float4 *dst = reinterpret_cast<float4 *>(out + (size_t)r * cout + cb * 16);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                           __uint_as_float(v[4 * j + 3]));
+                    if (bias) {
+                        o.x += __ldg(bias + cb * 16 + 4 * j); o.y += __ldg(bias + cb * 16 + 4 * j + 1);
+                        o.z += __ldg(bias + cb * 16 + 4 * j + 2); o.w += __ldg(bias + cb * 16 + 4 * j + 3);
+                    }
+                    dst[j] = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+}  // namespace cvb200
+
+using namespace cvb200;
+
+extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
+                                         int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVB_REQUIRE(cin > 0 && cin % kTcKB == 0 && cout >= 16 && cout <= 256 && cout % 16 == 0 && k3 > 0 && k3 <= kTcMaxK3,
+                CVB200_EINVAL, "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout <= 256, K^3 <= 32 (got %d, %d, %d)",
+                cin, cout, k3);
+    CVB_REQUIRE(n_out >= 0 && n_out < (1LL << 31), CVB200_EINVAL, "sc_conv_forward_tc: bad n_out");
+    if (n_out == 0) return 0;
+    CVB_REQUIRE(d_in && d_wt && d_nbr && d_out, CVB200_EINVAL, "sc_conv_forward_tc: NULL argument");
+    CVB_REQUIRE(((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_wt) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0,
+                CVB200_EINVAL, "sc_conv_forward_tc: 16-byte aligned feature / weight / output pointers required");
+    int tmem_cols = 32;
+    while (tmem_cols < cout) tmem_cols <<= 1;
+    const int nbr_bytes = ((k3 * kTcM * 4 + 1023) / 1024) * 1024;
+    const int stage_bytes = kTcM * 128 + cout * 128;
+    const unsigned grid = (unsigned)ceil_div(n_out, kTcM);
+    if (cout <= 64) {   // 4 stages of 24 KiB / 3 stages of <= 48 KiB: two CTAs per SM up to cout = 128
+        const size_t smem = 1024 + nbr_bytes + 4 * (size_t)stage_bytes;
+        static bool set4 = false;
+        if (!set4) {
+            CVB_CUDA(cudaFuncSetAttribute(sc_conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            set4 = true;
+        }
+        sc_conv_tc_kernel<4><<<grid, kTcThreads, smem, stream>>>(d_in, cin, d_wt, cout, d_nbr, (int)n_out, k3, d_bias, d_out, tmem_cols);
+    } else {
+        const size_t smem = 1024 + nbr_bytes + 3 * (size_t)stage_bytes;
+        static bool set3 = false;
+        if (!set3) {
+            CVB_CUDA(cudaFuncSetAttribute(sc_conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            set3 = true;
+        }
+        sc_conv_tc_kernel<3><<<grid, kTcThreads, smem, stream>>>(d_in, cin, d_wt, cout, d_nbr, (int)n_out, k3, d_bias, d_out, tmem_cols);
+    }
+    CVB_LAUNCH_CHECK("sc_conv_tc_kernel");
+    return 0;
+}

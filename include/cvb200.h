@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 5
+#define CVB200_ABI_VERSION 6
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -171,6 +171,12 @@ int cvb200_sc_kernel_map(const int32_t *d_out_coords, int64_t n_out, const void 
  * fp32 CUDA-core path (exact fp32 accumulation). */
 int cvb200_sc_conv_forward(const float *d_in, int32_t cin, const float *d_w, int32_t cout, const int32_t *d_nbr,
                            int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
+
+/* Same contraction on the tcgen05 tensor cores (kind::tf32, fp32 accumulation in tensor memory):
+ * d_wt is the weight PRE-TRANSPOSED to [k3, cout, cin].  Requires cin % 32 == 0, cout % 16 == 0,
+ * 16 <= cout <= 256, k3 <= 32 and 16-byte aligned pointers. */
+int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
+                              int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
 
 /* dW[k] [ca,cb] = sum_r A[ia(r,k),:]^T (x) B[ib(r,k),:] over the table rows r;
  * table_on_b = 0: ia = table[r,k], ib = r;  table_on_b = 1: ia = r, ib = table[r,k].  d_dw is overwritten. */

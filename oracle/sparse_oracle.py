@@ -138,3 +138,123 @@ class OracleNet:
             for blk in getattr(m, block):
                 f = self._block(blk, C, ts, f)
         return self._conv(m.final, C, ts, f)[1]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Vectorised CPU port (the timed `cpu_baseline` of the sparse-U-Net half in bench.py): same semantics as the
+# functions above, but kernel maps come from sorted packed keys + searchsorted and every offset is one
+# gather -> GEMM -> index_add_ -- which is how MinkowskiEngine's own CPU backend evaluates a convolution
+# [ME-recall].  tests/test_oracle_sparse.py checks it against the dict-based functions.
+def _pack(c):
+    c = c.long()
+    return ((c[:, 0] & 0xffff) << 48) | (((c[:, 1] + 32768) & 0xffff) << 32) | (((c[:, 2] + 32768) & 0xffff) << 16) | \
+        ((c[:, 3] + 32768) & 0xffff)
+
+
+class FastMaps:
+    """Per-scene coordinate levels and kernel maps (cached like ME's coordinate manager)."""
+
+    def __init__(self, coords):
+        self.levels = {1: coords.int()}
+        self._sorted, self._maps, self._down = {}, {}, {}
+
+    def _lookup(self, ts, query):
+        if ts not in self._sorted:
+            keys = _pack(self.levels[ts])
+            order = torch.argsort(keys)
+            self._sorted[ts] = (keys[order], order)
+        skeys, order = self._sorted[ts]
+        q = _pack(query)
+        pos = torch.searchsorted(skeys, q).clamp_(max=len(skeys) - 1)
+        hit = skeys[pos] == q
+        return order[pos], hit
+
+    def same(self, ts, K):
+        key = (ts, K)
+        if key not in self._maps:
+            c, h, pairs = self.levels[ts], K // 2, []
+            for k in range(K ** 3):
+                d = torch.tensor([0, (k % K - h) * ts, ((k // K) % K - h) * ts, (k // (K * K) - h) * ts], dtype=torch.int32)
+                j, hit = self._lookup(ts, c + d)
+                o = torch.nonzero(hit)[:, 0]
+                pairs.append((j[o], o))
+            self._maps[key] = pairs
+        return self._maps[key]
+
+    def down(self, ts):
+        if ts not in self._down:
+            c = self.levels[ts].long()
+            par = c.clone()
+            par[:, 1:] = torch.div(c[:, 1:], 2 * ts, rounding_mode="floor") * 2 * ts
+            keys = _pack(par)
+            uniq, inverse = torch.unique(keys, return_inverse=True)
+            first = torch.full((len(uniq),), len(keys), dtype=torch.long).scatter_reduce_(0, inverse, torch.arange(len(keys)), "amin")
+            order = torch.argsort(first)                      # number coarse voxels by their first child
+            rank = torch.empty_like(order); rank[order] = torch.arange(len(order))
+            parent = rank[inverse]
+            self.levels[2 * ts] = par[first[order]].int()
+            off = (c[:, 1:] - par[:, 1:]) // ts
+            self._down[ts] = (parent, off[:, 0] + 2 * (off[:, 1] + 2 * off[:, 2]))
+        return self._down[ts]
+
+
+class FastCpuNet(OracleNet):
+    """OracleNet with vectorised maps (float32, torch CPU threads)."""
+
+    def _conv(self, mod, maps, ts, f):
+        w = mod.kernel.detach().cpu()
+        b = mod.bias.detach().cpu() if mod.bias is not None else None
+        cout = w.shape[-1]
+        if mod.kernel_size == 1:
+            return ts, f @ w + (b if b is not None else 0)
+        if mod.is_transpose:
+            parent, koff = maps.down(ts // 2)
+            out = torch.zeros((len(parent), cout), dtype=f.dtype)
+            for k in range(8):
+                m = torch.nonzero(koff == k)[:, 0]
+                if len(m):
+                    out[m] = f[parent[m]] @ w[k]
+            return ts // 2, out + (b if b is not None else 0)
+        if mod.stride == 2:
+            parent, koff = maps.down(ts)
+            out = torch.zeros((maps.levels[2 * ts].shape[0], cout), dtype=f.dtype)
+            for k in range(8):
+                m = torch.nonzero(koff == k)[:, 0]
+                if len(m):
+                    out.index_add_(0, parent[m], f[m] @ w[k])
+            return 2 * ts, out + (b if b is not None else 0)
+        out = torch.zeros((f.shape[0], cout), dtype=f.dtype)
+        for k, (src, dst) in enumerate(maps.same(ts, mod.kernel_size)):
+            if len(src):
+                out.index_add_(0, dst, f[src] @ w[k])
+        return ts, out + (b if b is not None else 0)
+
+    def forward(self, coords, feats):
+        self_maps = FastMaps(coords.cpu())
+        return OracleNet.forward_with(self, self_maps, feats)
+
+
+def _forward_with(self, C, feats):
+    from canonicalvoting_b200.minkunet import _DECODER, _ENCODER
+    m = self.m
+    ts, f = self._conv(m.conv0p1s1, C, 1, feats.cpu())
+    f = torch.relu(self._bn(m.bn0, f))
+    skips = [f]
+    for conv, bn, block in _ENCODER:
+        ts, f = self._conv(getattr(m, conv), C, ts, f)
+        f = torch.relu(self._bn(getattr(m, bn), f))
+        for blk in getattr(m, block):
+            f = self._block(blk, C, ts, f)
+        skips.append(f)
+    skips.pop()
+    for conv, bn, block in _DECODER:
+        ts, f = self._conv(getattr(m, conv), C, ts, f)
+        f = torch.relu(self._bn(getattr(m, bn), f))
+        f = torch.cat([f, skips.pop()], 1)
+        for blk in getattr(m, block):
+            f = self._block(blk, C, ts, f)
+    return self._conv(m.final, C, ts, f)[1]
+
+
+OracleNet.forward_with = _forward_with
+OracleNet.forward = lambda self, coords, feats: _forward_with(self, {1: coords.cpu()}, feats)

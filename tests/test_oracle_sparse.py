@@ -114,3 +114,16 @@ def test_minkunet34c_structure_matches_the_reference_model():
     n_conv = sum(1 for k in sd if k.endswith("kernel"))
     n_bn = sum(1 for k in sd if k.endswith("bn.weight"))
     assert (n_conv, n_bn) == (63, 62)
+
+
+def test_fast_cpu_port_matches_dict_oracle():
+    """The vectorised CPU port timed by bench.py (cpu_baseline of the U-Net half) == the dict-based oracle."""
+    from canonicalvoting_b200.minkunet import MinkUNet14A
+    torch.manual_seed(0)
+    coords, feats, G, batch = _scene(n=400, G=16, batch=2, seed=5)
+    coords = coords.clone(); coords[:, 1:] -= 5
+    feats = feats.float()
+    model = MinkUNet14A(3, 12).eval()
+    a = SO.OracleNet(model).forward(coords, feats)
+    b = SO.FastCpuNet(model).forward(coords, feats)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)

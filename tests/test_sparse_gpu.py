@@ -142,3 +142,46 @@ def test_reference_row_order_and_errors():
         up(ME.SparseTensor(feats, coordinate_manager=st.coordinate_manager, tensor_stride=2))
     with pytest.raises(RuntimeError, match="no CPU path"):
         ME.SparseTensor(feats, coords, device="cpu")
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 64), (64, 64), (96, 96), (128, 96), (128, 128), (256, 256), (384, 256), (64, 16)])
+def test_tensor_core_conv_matches_fp32_path(cin, cout):
+    """tcgen05 kind::tf32 implicit GEMM vs the exact-fp32 CUDA-core kernel on the same tables: TF32 rounds the
+    inputs to 10 mantissa bits, accumulation is fp32 -> 3e-3 of the output scale."""
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200.sparse.functional import conv_table_forward
+    coords, _ = _scene(n=3000, G=20, batch=2, seed=cin + cout)
+    n = len(coords)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, cin, generator=g).cuda()
+    st = ME.SparseTensor(x, coords, device="cuda")
+    cm = st.coordinate_manager
+    d = cm.down(1)
+    nc = cm.levels[2].n
+    for name, table, n_in in (("same3", cm.kernel_map(1, 3), n), ("down", d["children"], n), ("up", d["up_table"], nc)):
+        k3 = table.shape[1]
+        xin = torch.randn(n_in, cin, generator=g).cuda()
+        w = (torch.randn(k3, cin, cout, generator=g) / (cin * 4) ** 0.5).cuda()
+        b = torch.randn(1, cout, generator=g).cuda() if name == "same3" else None
+        ref = conv_table_forward(xin, w, table, b, mode="fp32")
+        got = conv_table_forward(xin, w, table, b, mode="tf32")
+        torch.cuda.synchronize()
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert err <= 3e-3 * scale, "%s cin=%d cout=%d: max err %.3e vs scale %.3e" % (name, cin, cout, err, scale)
+        assert err > 0 or scale == 0          # it really is a different arithmetic path
+
+
+def test_tensor_core_tail_tile_and_empty_rows():
+    from canonicalvoting_b200.sparse.functional import conv_table_forward
+    g = torch.Generator().manual_seed(3)
+    n_in, n_out, cin, cout = 500, 130, 64, 32            # 130 rows: a full tile + a 2-row tail tile
+    table = torch.randint(-1, n_in, (n_out, 27), generator=g, dtype=torch.int64).int()
+    table[5] = -1                                          # a row without any neighbour -> exact zeros
+    table[:, 20:] = -1                                     # offsets nobody uses are skipped
+    x = torch.randn(n_in, cin, generator=g).cuda()
+    w = torch.randn(27, cin, cout, generator=g).cuda() * 0.1
+    ref = conv_table_forward(x, w, table.cuda(), None, mode="fp32")
+    got = conv_table_forward(x, w, table.cuda(), None, mode="tf32")
+    assert float((got - ref).abs().max()) <= 3e-3 * float(ref.abs().max())
+    assert float(got[5].abs().max()) == 0.0
