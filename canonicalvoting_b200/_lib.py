@@ -30,7 +30,7 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class BpParams(ctypes.Structure):
@@ -57,6 +57,20 @@ SIGNATURES.update({
     "cvb200_sc_conv_forward": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
     "cvb200_sc_conv_forward_tc": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
+})
+
+
+
+class ScOp(ctypes.Structure):
+    """cvb200_sc_op (include/cvb200.h)."""
+    _fields_ = [("kind", _i32), ("cin", _i32), ("cout", _i32), ("k3", _i32), ("ldi", _i32), ("ldo", _i32), ("ldr", _i32),
+                ("relu", _i32), ("n_out", _i64), ("in_", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("table", _vp),
+                ("out", _vp)]
+
+
+SIGNATURES.update({
+    "cvb200_sc_run_program": (ctypes.c_int, [ctypes.POINTER(ScOp), _i32, _vp]),
+    "cvb200_head_decode": (ctypes.c_int, [_f, _i32, _i64, _i32, _i32, _f, _f, _vp, _f, _vp]),
 })
 
 _lib = None

@@ -83,8 +83,12 @@ struct TcSmemHeader {
 // dynamic smem: [header 1 KiB][nbr tile: K3 x 128 ints, padded to 1 KiB][stages x (A tile 16 KiB | B tile N x 128 B)]
 template <int kStages>
 __global__ void __launch_bounds__(kTcThreads)
-sc_conv_tc_kernel(const float *__restrict__ in, int cin, const float *__restrict__ wt, int cout, const int *__restrict__ nbr,
-                  int n_out, int k3, const float *__restrict__ bias, float *__restrict__ out, int tmem_cols) {
+sc_conv_tc_kernel(const float *__restrict__ in, int ldi, int cin, const float *__restrict__ wt, int cout_total,
+                  const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias, const float *__restrict__ residual,
+                  int ldr, int relu, float *__restrict__ out, int ldo, int tmem_cols, int cout) {
+    // grid = (row tiles, channel splits, offset splits): this CTA produces out[row tile, n0 .. n0+cout) from the kernel
+    // offsets k with k % gridDim.z == blockIdx.z (partial sums of different offset splits are combined with float atomics)
+    const int n0 = blockIdx.y * cout;
     extern __shared__ __align__(1024) unsigned char smem[];
     TcSmemHeader &H = *reinterpret_cast<TcSmemHeader *>(smem);
     int *s_nbr = reinterpret_cast<int *>(smem + 1024);
@@ -101,7 +105,7 @@ sc_conv_tc_kernel(const float *__restrict__ in, int cin, const float *__restrict
         const int r = e / k3, k = e - r * k3;   // consecutive threads read consecutive table entries
         const int v = row0 + r < n_out ? __ldg(nbr + (size_t)(row0 + r) * k3 + k) : -1;
         s_nbr[k * kTcM + r] = v;
-        if (v >= 0) H.any[k] = 1;               // benign race
+        if (v >= 0 && k % (int)gridDim.z == (int)blockIdx.z) H.any[k] = 1;   // benign race
     }
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&H.empty_bar[s]), 1);
@@ -136,11 +140,11 @@ sc_conv_tc_kernel(const float *__restrict__ in, int cin, const float *__restrict
         for (int e = tid; e < kTcM * 8; e += kTcThreads) {
             const int r = e >> 3, c = e & 7;
             const int src_row = idx[r];
-            const float *src = in + (size_t)(src_row >= 0 ? src_row : 0) * cin + c0 + c * 4;
+            const float *src = in + (size_t)(src_row >= 0 ? src_row : 0) * ldi + c0 + c * 4;
             cp_async16(a_s + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src, src_row >= 0 ? 16u : 0u);
         }
         // B: cout rows (output channels) x 8 chunks: Wt[k][n][c0 .. c0+32)
-        const float *wk = wt + (size_t)k * cout * cin + c0;
+        const float *wk = wt + ((size_t)k * cout_total + n0) * cin + c0;
         for (int e = tid; e < cout * 8; e += kTcThreads) {
             const int r = e >> 3, c = e & 7;
             cp_async16(b_s + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), wk + (size_t)r * cin + c * 4, 16u);
@@ -197,17 +201,27 @@ sc_conv_tc_kernel(const float *__restrict__ in, int cin, const float *__restrict
 #pragma unroll
                 for (int j = 0; j < 16; j++) v[j] = 0u;
             }
-            if (r < n_out) {
-                float4 *dst = reinterpret_cast<float4 *>(out + (size_t)r * cout + cb * 16);
+            if (r < n_out && (total > 0 || gridDim.z == 1 || (bias != nullptr && blockIdx.z == 0))) {
+                float *dst = out + (size_t)r * ldo + n0 + cb * 16;
+                const bool add_bias = bias != nullptr && blockIdx.z == 0;
+                const float *res = residual ? residual + (size_t)r * ldr + n0 + cb * 16 : nullptr;   // only with gridDim.z == 1
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                            __uint_as_float(v[4 * j + 3]));
-                    if (bias) {
-                        o.x += __ldg(bias + cb * 16 + 4 * j); o.y += __ldg(bias + cb * 16 + 4 * j + 1);
-                        o.z += __ldg(bias + cb * 16 + 4 * j + 2); o.w += __ldg(bias + cb * 16 + 4 * j + 3);
+                    if (add_bias) {
+                        const float *bp = bias + n0 + cb * 16 + 4 * j;
+                        o.x += __ldg(bp); o.y += __ldg(bp + 1); o.z += __ldg(bp + 2); o.w += __ldg(bp + 3);
                     }
-                    dst[j] = o;
+                    if (res) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4 *>(res) + j);
+                        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                    }
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (gridDim.z == 1)
+                        reinterpret_cast<float4 *>(dst)[j] = o;
+                    else   // split over kernel offsets: out was zero-filled by the host wrapper
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
                 }
             }
         }
@@ -217,34 +231,63 @@ sc_conv_tc_kernel(const float *__restrict__ in, int cin, const float *__restrict
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
 }
 
-}  // namespace cvb200
+// finishing pass of a convolution whose kernel offsets were split over several CTAs (partial sums combined with
+// atomics): out = [relu](out + bias + residual)
+__global__ void sc_finish_kernel(float *__restrict__ out, int ldo, int n, int cout, const float *__restrict__ bias,
+                                 const float *__restrict__ residual, int ldr, int relu) {
+    const int c4 = cout / 4;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * c4) return;
+    const int r = (int)(t / c4), c = (int)(t % c4) * 4;
+    float4 o = *reinterpret_cast<float4 *>(out + (size_t)r * ldo + c);
+    if (bias) { o.x += __ldg(bias + c); o.y += __ldg(bias + c + 1); o.z += __ldg(bias + c + 2); o.w += __ldg(bias + c + 3); }
+    if (residual) {
+        const float4 rv = __ldg(reinterpret_cast<const float4 *>(residual + (size_t)r * ldr + c));
+        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4 *>(out + (size_t)r * ldo + c) = o;
+}
 
-using namespace cvb200;
-
-extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
-                                         int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// out[o, 0:cout) (row stride ldo) = [relu]( sum_k in[nbr[o,k], 0:cin) (row stride ldi) @ Wt[k]^T + bias + residual )
+int launch_conv_tc(const float *d_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out, int k3,
+                   const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream) {
     CVB_REQUIRE(cin > 0 && cin % kTcKB == 0 && cout >= 16 && cout <= 256 && cout % 16 == 0 && k3 > 0 && k3 <= kTcMaxK3,
-                CVB200_EINVAL, "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout <= 256, K^3 <= 32 (got %d, %d, %d)",
-                cin, cout, k3);
+                CVB200_EINVAL, "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout <= 256, K^3 <= %d (got %d, %d, %d)",
+                kTcMaxK3, cin, cout, k3);
     CVB_REQUIRE(n_out >= 0 && n_out < (1LL << 31), CVB200_EINVAL, "sc_conv_forward_tc: bad n_out");
     if (n_out == 0) return 0;
     CVB_REQUIRE(d_in && d_wt && d_nbr && d_out, CVB200_EINVAL, "sc_conv_forward_tc: NULL argument");
-    CVB_REQUIRE(((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_wt) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0,
-                CVB200_EINVAL, "sc_conv_forward_tc: 16-byte aligned feature / weight / output pointers required");
+    CVB_REQUIRE(((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_wt) | reinterpret_cast<uintptr_t>(d_out) |
+                  reinterpret_cast<uintptr_t>(d_res)) & 15) == 0 && ldi % 4 == 0 && ldo % 4 == 0 && ldr % 4 == 0,
+                CVB200_EINVAL, "sc_conv_forward_tc: 16-byte aligned pointers and row strides required");
+    // Small levels of the U-Net have only a handful of 128-row tiles: split the output channels (64 per CTA) and the
+    // kernel offsets over more CTAs until the grid covers the 148 SMs.
+    const int m_tiles = (int)ceil_div(n_out, kTcM);
+    int n_splits = 1, k_splits = 1;
+    if (m_tiles < kNumSMs / 2 && cout >= 128 && cout % 64 == 0) n_splits = cout / 64;
+    const int kmul = (k3 % 3 == 0) ? 3 : 2, cblocks = cin / kTcKB;
+    while (m_tiles * n_splits * k_splits < kNumSMs && k_splits * kmul <= k3 && (k3 / (k_splits * kmul)) * cblocks >= 8)
+        k_splits *= kmul;   // keep at least 8 k-blocks per CTA so that the prologue stays amortised
+    const int nc = cout / n_splits;
     int tmem_cols = 32;
-    while (tmem_cols < cout) tmem_cols <<= 1;
+    while (tmem_cols < nc) tmem_cols <<= 1;
     const int nbr_bytes = ((k3 * kTcM * 4 + 1023) / 1024) * 1024;
-    const int stage_bytes = kTcM * 128 + cout * 128;
-    const unsigned grid = (unsigned)ceil_div(n_out, kTcM);
-    if (cout <= 64) {   // 4 stages of 24 KiB / 3 stages of <= 48 KiB: two CTAs per SM up to cout = 128
+    const int stage_bytes = kTcM * 128 + nc * 128;
+    const dim3 grid((unsigned)m_tiles, (unsigned)n_splits, (unsigned)k_splits);
+    const bool split = k_splits > 1;
+    if (split) CVB_CUDA(cudaMemset2DAsync(d_out, sizeof(float) * (size_t)ldo, 0, sizeof(float) * (size_t)cout, (size_t)n_out, stream));
+    const float *k_bias = split ? nullptr : d_bias, *k_res = split ? nullptr : d_res;
+    const int k_relu = split ? 0 : relu;
+    if (nc <= 64) {   // 4 stages of 24 KiB / 3 stages of <= 48 KiB: two CTAs per SM up to 128 channels per CTA
         const size_t smem = 1024 + nbr_bytes + 4 * (size_t)stage_bytes;
         static bool set4 = false;
         if (!set4) {
             CVB_CUDA(cudaFuncSetAttribute(sc_conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             set4 = true;
         }
-        sc_conv_tc_kernel<4><<<grid, kTcThreads, smem, stream>>>(d_in, cin, d_wt, cout, d_nbr, (int)n_out, k3, d_bias, d_out, tmem_cols);
+        sc_conv_tc_kernel<4><<<grid, kTcThreads, smem, stream>>>(d_in, ldi, cin, d_wt, cout, d_nbr, (int)n_out, k3, k_bias, k_res, ldr,
+                                                                 k_relu, d_out, ldo, tmem_cols, nc);
     } else {
         const size_t smem = 1024 + nbr_bytes + 3 * (size_t)stage_bytes;
         static bool set3 = false;
@@ -252,8 +295,22 @@ extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const f
             CVB_CUDA(cudaFuncSetAttribute(sc_conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             set3 = true;
         }
-        sc_conv_tc_kernel<3><<<grid, kTcThreads, smem, stream>>>(d_in, cin, d_wt, cout, d_nbr, (int)n_out, k3, d_bias, d_out, tmem_cols);
+        sc_conv_tc_kernel<3><<<grid, kTcThreads, smem, stream>>>(d_in, ldi, cin, d_wt, cout, d_nbr, (int)n_out, k3, k_bias, k_res, ldr,
+                                                                 k_relu, d_out, ldo, tmem_cols, nc);
     }
     CVB_LAUNCH_CHECK("sc_conv_tc_kernel");
+    if (split && (d_bias || d_res || relu)) {
+        const long long total = (long long)n_out * (cout / 4);
+        sc_finish_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(d_out, ldo, (int)n_out, cout, d_bias, d_res, ldr, relu);
+        CVB_LAUNCH_CHECK("sc_finish_kernel");
+    }
     return 0;
+}
+}  // namespace cvb200
+
+using namespace cvb200;
+
+extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
+                                         int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream_) {
+    return launch_conv_tc(d_in, cin, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, nullptr, 0, 0, d_out, cout, (cudaStream_t)stream_);
 }

@@ -1,0 +1,135 @@
+// canonicalvoting_b200/csrc/sparse_engine.cu -- inference executor of the sparse-voxel U-Net + head decode.
+//
+// The reference's eval path runs utils/minkunet.py:122-180 layer by layer from Python: per convolution a
+// MinkowskiEngine call, then BatchNorm, ReLU, residual add and ME.cat as separate torch kernels
+// (eval_joint.py:169-171), followed by ~10 small torch ops for the head decode (eval_joint.py:173-190).
+// Here the host side compiles the network ONCE into a flat program of fused convolution ops
+//     out[:, c0:c0+cout] = [relu]( conv(in[:, a0:a0+cin]) + bias + residual )
+// (BatchNorm folded into weights / bias, ME.cat realised by writing into column slices of a shared buffer)
+// and this file launches the whole program back to back from C++ -- no interpreter between kernels.
+#include "common.cuh"
+
+namespace cvb200 {
+
+int launch_conv_tc(const float *d_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out, int k3,
+                   const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream);
+
+// Convolution with a tiny input width (the 3-channel 5^3 stem, utils/minkunet.py:53): one warp per output row, the
+// whole kernel (K^3 x cin x cout) in shared memory, lanes = output channels; neighbour ids are read 32 at a time and
+// only existing neighbours are visited.
+constexpr int kStemThreads = 256;
+
+__global__ void __launch_bounds__(kStemThreads)
+sc_conv_smallcin_kernel(const float *__restrict__ in, int ldi, int cin, const float *__restrict__ w /*[k3][cin][cout]*/, int cout,
+                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias, int relu,
+                        float *__restrict__ out, int ldo) {
+    extern __shared__ float s_w[];
+    for (int e = threadIdx.x; e < k3 * cin * cout; e += kStemThreads) s_w[e] = __ldg(w + e);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nj = cout / 32;   // <= 4
+    for (int r = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5); r < n_out; r += gridDim.x * (kStemThreads / 32)) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = 0; k0 < k3; k0 += 32) {
+            const int mine = k0 + lane < k3 ? __ldg(nbr + (size_t)r * k3 + k0 + lane) : -1;
+            unsigned m = __ballot_sync(0xffffffffu, mine >= 0);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int src = __shfl_sync(0xffffffffu, mine, b);
+                const float *x = in + (size_t)src * ldi;
+                const float *wk = s_w + (size_t)(k0 + b) * cin * cout;
+                for (int c = 0; c < cin; c++) {
+                    const float xv = __ldg(x + c);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < nj) acc[j] = fmaf(xv, wk[c * cout + lane + 32 * j], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < nj) {
+                float o = acc[j] + (bias ? __ldg(bias + lane + 32 * j) : 0.f);
+                if (relu) o = fmaxf(o, 0.f);
+                out[(size_t)r * ldo + lane + 32 * j] = o;
+            }
+    }
+}
+
+// Head decode of the joint model (eval_joint.py:173-190): one thread per point.
+//   feats [n, 6*C + C + 1]: xyz[C][3] | scale[C][3] | class logits [C+1] (last = background)
+__global__ void head_decode_kernel(const float *__restrict__ f, int ld, int n, int nclasses, int log_scale,
+                                   float *__restrict__ xyz, float *__restrict__ scale, long long *__restrict__ cls,
+                                   float *__restrict__ prob) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *row = f + (size_t)i * ld;
+    const float *logit = row + 6 * nclasses;
+    float best = -INFINITY, best_obj = -INFINITY;
+    int k = 0, k_obj = 0;
+    for (int c = 0; c <= nclasses; c++) {          // first maximum, like torch.argmax
+        const float v = __ldg(logit + c);
+        if (v > best) { best = v; k = c; }
+        if (c < nclasses && v > best_obj) { best_obj = v; k_obj = c; }
+    }
+    float sum = 0.f;
+    for (int c = 0; c <= nclasses; c++) sum += expf(__ldg(logit + c) - best);
+    if (k == nclasses) k = 0;                      // class_label_idx[class_label_idx == nclasses] = 0  (:178)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        xyz[3 * (size_t)i + d] = __ldg(row + 3 * k + d);
+        const float s = __ldg(row + 3 * nclasses + 3 * k + d);
+        scale[3 * (size_t)i + d] = log_scale ? expf(s) : s;
+    }
+    cls[i] = k_obj;                                // argmax over the object classes          (:188)
+    prob[i] = expf(best_obj - best) / sum;         // max softmax over the object classes     (:189)
+}
+
+}  // namespace cvb200
+
+using namespace cvb200;
+
+extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVB_REQUIRE(ops && n_ops >= 0, CVB200_EINVAL, "sc_run_program: NULL program");
+    for (int i = 0; i < n_ops; i++) {
+        const cvb200_sc_op &o = ops[i];
+        if (o.kind == CVB200_OP_CONV_TC) {
+            const int rc = launch_conv_tc(o.in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr, o.relu,
+                                          o.out, o.ldo, stream);
+            if (rc) return rc;
+        } else if (o.kind == CVB200_OP_CONV_SMALLCIN) {
+            CVB_REQUIRE(o.cin >= 1 && o.cin <= 8 && o.cout % 32 == 0 && o.cout <= 128 && !o.residual, CVB200_EINVAL,
+                        "sc_run_program: op %d: small-cin convolution needs cin <= 8, cout in {32,64,96,128}, no residual", i);
+            const size_t smem = sizeof(float) * (size_t)o.k3 * o.cin * o.cout;
+            CVB_REQUIRE(smem <= 160 * 1024, CVB200_EINVAL, "sc_run_program: op %d: kernel does not fit shared memory", i);
+            static bool set = false;
+            if (!set) {
+                CVB_CUDA(cudaFuncSetAttribute(sc_conv_smallcin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                set = true;
+            }
+            if (o.n_out > 0) {
+                const int blocks = (int)std::min<int64_t>(2 * kNumSMs, ceil_div(o.n_out, kStemThreads / 32));
+                sc_conv_smallcin_kernel<<<blocks, kStemThreads, smem, stream>>>(o.in, o.ldi, o.cin, o.w, o.cout, o.table, (int)o.n_out,
+                                                                               o.k3, o.bias, o.relu, o.out, o.ldo);
+                CVB_LAUNCH_CHECK("sc_conv_smallcin_kernel");
+            }
+        } else {
+            CVB_REQUIRE(false, CVB200_EINVAL, "sc_run_program: op %d has unknown kind %d", i, o.kind);
+        }
+    }
+    return 0;
+}
+
+extern "C" int cvb200_head_decode(const float *d_feats, int32_t ld, int64_t n, int32_t nclasses, int32_t log_scale, float *d_xyz,
+                                  float *d_scale, int64_t *d_class, float *d_prob, void *stream_) {
+    CVB_REQUIRE(n >= 0 && n < (1LL << 31) && nclasses >= 1 && nclasses <= 64 && ld >= 7 * nclasses + 1, CVB200_EINVAL,
+                "head_decode: bad sizes (n=%lld, nclasses=%d, ld=%d)", (long long)n, nclasses, ld);
+    if (n == 0) return 0;
+    CVB_REQUIRE(d_feats && d_xyz && d_scale && d_class && d_prob, CVB200_EINVAL, "head_decode: NULL argument");
+    head_decode_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream_>>>(d_feats, ld, (int)n, nclasses, log_scale, d_xyz,
+                                                                                     d_scale, (long long *)d_class, d_prob);
+    CVB_LAUNCH_CHECK("head_decode_kernel");
+    return 0;
+}

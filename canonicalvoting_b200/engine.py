@@ -1,0 +1,216 @@
+"""MinkUNetEngine -- inference executor for the reference's sparse U-Net (eval path: eval_joint.py:151-190).
+
+The module-by-module path (canonicalvoting_b200.sparse / the `MinkowskiEngine` compat package) mirrors the
+reference's Python structure and is what training uses.  For inference this engine compiles the SAME
+network (any `MinkUNetBase`-shaped model: ours or the reference's own utils/minkunet.py class running on the
+compat package) into a flat program of fused convolution ops executed back to back by
+`cvb200_sc_run_program` (csrc/sparse_engine.cu):
+
+  * BatchNorm (eval mode) is folded into the convolution weights and a bias  (utils/minkunet.py:123-124 ...);
+  * ReLU and the residual add of BasicBlock run in the convolution epilogue;
+  * `ME.cat(out, skip)` (utils/minkunet.py:153-177) costs nothing: the encoder writes its skip tensor and the
+    transposed convolution writes its output into column slices of one pre-allocated buffer;
+  * 1x1x1 convolutions (block down-samples, `final`) use the same tensor-core kernel with an identity table;
+  * the head decode (eval_joint.py:173-190) is one kernel.
+
+    engine = MinkUNetEngine(model)                     # after load_state_dict(...), model.eval()
+    feats = engine(coords_int32_cuda, feats_cuda)      # == model(ME.SparseTensor(feats, coords)).F up to TF32 rounding
+    xyz, scale, class_pred, prob = engine.predict(coords, feats)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .sparse.coords import CoordinateManager, _ptr, _stream
+
+_ENCODER = [("conv1p1s2", "bn1", "block1"), ("conv2p2s2", "bn2", "block2"), ("conv3p4s2", "bn3", "block3"),
+            ("conv4p8s2", "bn4", "block4")]
+_DECODER = [("convtr4p16s2", "bntr4", "block5"), ("convtr5p8s2", "bntr5", "block6"), ("convtr6p4s2", "bntr6", "block7"),
+            ("convtr7p2s2", "bntr7", "block8")]
+
+
+def _fold(conv, bn):
+    """(weight [k3, cin, cout] with the BatchNorm scale folded in, bias [cout] or None) as float32 tensors."""
+    w = conv.kernel.detach().float()
+    if w.dim() == 2:
+        w = w.unsqueeze(0)
+    b = conv.bias.detach().float().view(-1) if conv.bias is not None else None
+    if bn is not None:
+        n = bn.bn
+        g = n.weight.detach().float() / torch.sqrt(n.running_var.float() + n.eps)
+        w = w * g.view(1, 1, -1)
+        shift = n.bias.detach().float() - n.running_mean.float() * g
+        b = shift if b is None else b * g + shift
+    return w, b
+
+
+class _Slice:
+    """Column slice [c0, c0+c) of a row-major float32 buffer [n, ld]."""
+
+    def __init__(self, buf, c0, c):
+        self.buf, self.c0, self.c = buf, c0, c
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 4 * self.c0
+
+    @property
+    def ld(self):
+        return self.buf.shape[1]
+
+    def tensor(self):
+        return self.buf[:, self.c0:self.c0 + self.c]
+
+
+class MinkUNetEngine:
+    def __init__(self, model, nclasses=9, log_scale=True):
+        self.nclasses, self.log_scale = nclasses, log_scale
+        self.model = model
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("MinkUNetEngine needs the model on a CUDA device (no CPU path)")
+        self.refresh()
+
+    def refresh(self):
+        """(Re)pack the model's parameters: call again after the weights changed."""
+        m = self.model
+        self.w = {}
+
+        def put(name, conv, bn):
+            w, b = _fold(conv, bn)
+            cin = w.shape[1]
+            if cin % 32 == 0:       # tensor-core op: [k3, cout, cin]
+                self.w[name] = (w.transpose(1, 2).contiguous(), b.contiguous() if b is not None else None, 0)
+            else:                   # small-cin op keeps [k3, cin, cout]
+                self.w[name] = (w.contiguous(), b.contiguous() if b is not None else None, 1)
+
+        put("conv0p1s1", m.conv0p1s1, m.bn0)
+        for conv, bn, block in _ENCODER + _DECODER:
+            put(conv, getattr(m, conv), getattr(m, bn))
+            for i, blk in enumerate(getattr(m, block)):
+                put("%s.%d.conv1" % (block, i), blk.conv1, blk.norm1)
+                put("%s.%d.conv2" % (block, i), blk.conv2, blk.norm2)
+                if blk.downsample is not None:
+                    put("%s.%d.down" % (block, i), blk.downsample[0], blk.downsample[1])
+        put("final", m.final, None)
+        self.planes = {block: [getattr(m, block)[0].conv1.out_channels, len(getattr(m, block))] for _, _, block in _ENCODER + _DECODER}
+        self.init_dim = m.conv0p1s1.out_channels
+        self.out_channels = m.final.out_channels
+
+    # ------------------------------------------------------------------ program construction
+    def _op(self, ops, name, src, dst, table, relu, residual=None):
+        w, b, kind = self.w[name]
+        k3 = w.shape[0]
+        cin, cout = (w.shape[2], w.shape[1]) if kind == 0 else (w.shape[1], w.shape[2])
+        assert src.c == cin and dst.c == cout and table.shape[1] == k3, (name, src.c, cin, dst.c, cout, table.shape, k3)
+        o = _lib.ScOp()
+        o.kind, o.cin, o.cout, o.k3 = kind, cin, cout, k3
+        o.ldi, o.ldo, o.ldr, o.relu = src.ld, dst.ld, residual.ld if residual is not None else 0, 1 if relu else 0
+        o.n_out = table.shape[0]
+        o.in_, o.w, o.bias = src.ptr, w.data_ptr(), b.data_ptr() if b is not None else None
+        o.residual = residual.ptr if residual is not None else None
+        o.table, o.out = table.data_ptr(), dst.ptr
+        ops.append(o)
+
+    def _blocks(self, ops, keep, block, cm, ts, x, out_slice=None):
+        """BasicBlocks of one stage; the last block writes into `out_slice` (a skip slot) when given."""
+        planes, nblk = self.planes[block]
+        n = cm.levels[ts].n
+        nbr = cm.kernel_map(ts, 3)
+        ident = self._identity(cm, ts)
+        for i in range(nblk):
+            t1 = _Slice(torch.empty((n, planes), dtype=torch.float32, device=self.device), 0, planes)
+            keep.append(t1.buf)
+            self._op(ops, "%s.%d.conv1" % (block, i), x, t1, nbr, relu=True)
+            res = x
+            if ("%s.%d.down" % (block, i)) in self.w:
+                res = _Slice(torch.empty((n, planes), dtype=torch.float32, device=self.device), 0, planes)
+                keep.append(res.buf)
+                self._op(ops, "%s.%d.down" % (block, i), x, res, ident, relu=False)
+            if i == nblk - 1 and out_slice is not None:
+                dst = out_slice
+            else:
+                dst = _Slice(torch.empty((n, planes), dtype=torch.float32, device=self.device), 0, planes)
+                keep.append(dst.buf)
+            self._op(ops, "%s.%d.conv2" % (block, i), t1, dst, nbr, relu=True, residual=res)
+            x = dst
+        return x
+
+    def _identity(self, cm, ts):
+        key = ("ident", ts)
+        t = cm._nbr.get(key)
+        if t is None:
+            t = torch.arange(cm.levels[ts].n, dtype=torch.int32, device=self.device).view(-1, 1).contiguous()
+            cm._nbr[key] = t
+        return t
+
+    def build(self, coords, feats):
+        """Coordinate maps + buffers + program for one batch of scenes. Returns (ops array, output slice, keep-alive list)."""
+        cm = CoordinateManager(coords)
+        dev, f32 = self.device, torch.float32
+        ts_list = [1, 2, 4, 8, 16]
+        for ts in ts_list[:-1]:
+            cm.down(ts)
+        n = {ts: cm.levels[ts].n for ts in ts_list}
+        P = self.planes
+        ops, keep = [], [cm, feats]
+        # concat buffers of the decoder: [transposed-conv output | encoder skip]
+        dec_planes = {8: P["block5"][0], 4: P["block6"][0], 2: P["block7"][0], 1: P["block8"][0]}
+        tr_out = {8: self.w["convtr4p16s2"][0].shape[1], 4: self.w["convtr5p8s2"][0].shape[1],
+                  2: self.w["convtr6p4s2"][0].shape[1], 1: self.w["convtr7p2s2"][0].shape[1]}
+        skip_c = {8: P["block3"][0], 4: P["block2"][0], 2: P["block1"][0], 1: self.init_dim}
+        cat = {ts: torch.empty((n[ts], tr_out[ts] + skip_c[ts]), dtype=f32, device=dev) for ts in (1, 2, 4, 8)}
+        keep += list(cat.values())
+        skip = {ts: _Slice(cat[ts], tr_out[ts], skip_c[ts]) for ts in cat}
+        # stem: conv0 (5^3, stride 1) + bn0 + relu -> skip slot of level 1
+        src = _Slice(feats.contiguous(), 0, feats.shape[1])
+        self._op(ops, "conv0p1s1", src, skip[1], cm.kernel_map(1, self.model.conv0p1s1.kernel_size), relu=True)
+        x, ts = skip[1], 1
+        for (conv, bn, block), skip_ts in zip(_ENCODER, (2, 4, 8, None)):
+            d = cm.down(ts)
+            cout = self.w[conv][0].shape[1]
+            y = _Slice(torch.empty((n[2 * ts], cout), dtype=f32, device=dev), 0, cout)
+            keep.append(y.buf)
+            self._op(ops, conv, x, y, d["children"], relu=True)
+            ts *= 2
+            x = self._blocks(ops, keep, block, cm, ts, y, skip[skip_ts] if skip_ts is not None else None)
+        for (conv, bn, block), fine in zip(_DECODER, (8, 4, 2, 1)):
+            d = cm._down[fine]
+            self._op(ops, conv, x, _Slice(cat[fine], 0, tr_out[fine]), d["up_table"], relu=True)
+            ts = fine
+            x = self._blocks(ops, keep, block, cm, ts, _Slice(cat[fine], 0, cat[fine].shape[1]))
+        out = _Slice(torch.empty((n[1], self.out_channels), dtype=f32, device=dev), 0, self.out_channels)
+        self._op(ops, "final", x, out, self._identity(cm, 1), relu=False)
+        arr = (_lib.ScOp * len(ops))(*ops)
+        return arr, out, keep
+
+    # ------------------------------------------------------------------ execution
+    def __call__(self, coords, feats):
+        """coords int32 [N,4] (batch,x,y,z) and feats float32 [N,Cin] on the device -> features [N, Cout]."""
+        if not (coords.is_cuda and feats.is_cuda):
+            raise RuntimeError("MinkUNetEngine: CUDA tensors expected (there is no CPU path)")
+        L = _lib.load()
+        with torch.cuda.device(self.device):
+            arr, out, keep = self.build(coords.to(torch.int32).contiguous(), feats.float())
+            rc = L.cvb200_sc_run_program(arr, len(arr), _stream())
+            _lib.check(rc, "cvb200_sc_run_program")
+        self._keep = keep      # buffers must outlive the asynchronous launches
+        return out.buf
+
+    def decode(self, feats):
+        """Head decode (eval_joint.py:173-190): features [N, 7*C+1] -> (xyz_pred, scale_pred, class_pred int64, prob_pred)."""
+        L = _lib.load()
+        n = feats.shape[0]
+        xyz = torch.empty((n, 3), dtype=torch.float32, device=feats.device)
+        scale = torch.empty((n, 3), dtype=torch.float32, device=feats.device)
+        cls = torch.empty((n,), dtype=torch.int64, device=feats.device)
+        prob = torch.empty((n,), dtype=torch.float32, device=feats.device)
+        with torch.cuda.device(feats.device):
+            rc = L.cvb200_head_decode(_ptr(feats), feats.stride(0), n, self.nclasses, 1 if self.log_scale else 0, _ptr(xyz),
+                                      _ptr(scale), _ptr(cls), _ptr(prob), _stream())
+            _lib.check(rc, "cvb200_head_decode")
+        return xyz, scale, cls, prob
+
+    def predict(self, coords, feats):
+        return self.decode(self(coords, feats))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 6
+#define CVB200_ABI_VERSION 7
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -177,6 +177,35 @@ int cvb200_sc_conv_forward(const float *d_in, int32_t cin, const float *d_w, int
  * 16 <= cout <= 256, k3 <= 32 and 16-byte aligned pointers. */
 int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
                               int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
+
+/* One fused convolution of an inference program (cvb200_sc_run_program):
+ *   out[:, 0:cout) (row stride ldo) = [relu]( sum_k in[table[o,k], 0:cin) (row stride ldi) @ W[k] + bias + residual )
+ * `in`, `out` and `residual` may point into column slices of wider buffers (that is how ME.cat,
+ * utils/minkunet.py:153-177, costs nothing).  kind CVB200_OP_CONV_TC: tcgen05 path, w = [k3,cout,cin]
+ * (pre-transposed, BatchNorm folded in), cin % 32 == 0, cout % 16 == 0;  kind CVB200_OP_CONV_SMALLCIN:
+ * CUDA-core path for the 3-channel stem, w = [k3,cin,cout], cin <= 8, cout % 32 == 0. */
+#define CVB200_OP_CONV_TC 0
+#define CVB200_OP_CONV_SMALLCIN 1
+typedef struct cvb200_sc_op {
+    int32_t kind, cin, cout, k3;
+    int32_t ldi, ldo, ldr, relu;
+    int64_t n_out;
+    const float *in;
+    const float *w;
+    const float *bias;       /* [cout] or NULL */
+    const float *residual;   /* [n_out, cout] with row stride ldr, or NULL */
+    const int32_t *table;    /* [n_out, k3] neighbour table */
+    float *out;
+} cvb200_sc_op;
+
+/* Launch the ops of a program in order on `stream` (host array of ops; asynchronous). */
+int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, void *stream);
+
+/* Head decode of the joint model (eval_joint.py:173-190): d_feats [n, >= 7*nclasses+1] (row stride ld) =
+ * xyz[C][3] | scale[C][3] | logits[C+1] -> xyz_pred [n,3], scale_pred [n,3] (exp() if log_scale,
+ * config/config.yaml:17), class_pred [n] int64 (argmax over the C object classes), prob_pred [n]. */
+int cvb200_head_decode(const float *d_feats, int32_t ld, int64_t n, int32_t nclasses, int32_t log_scale, float *d_xyz,
+                       float *d_scale, int64_t *d_class, float *d_prob, void *stream);
 
 /* dW[k] [ca,cb] = sum_r A[ia(r,k),:]^T (x) B[ib(r,k),:] over the table rows r;
  * table_on_b = 0: ia = table[r,k], ib = r;  table_on_b = 1: ia = r, ib = table[r,k].  d_dw is overwritten. */

@@ -185,3 +185,37 @@ def test_tensor_core_tail_tile_and_empty_rows():
     got = conv_table_forward(x, w, table.cuda(), None, mode="tf32")
     assert float((got - ref).abs().max()) <= 3e-3 * float(ref.abs().max())
     assert float(got[5].abs().max()) == 0.0
+
+
+def test_engine_matches_module_path_and_oracle():
+    """MinkUNetEngine (fused program, BN folded, TF32 tensor cores) vs the module-by-module fp32 path and the CPU oracle."""
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200.engine import MinkUNetEngine
+    from canonicalvoting_b200.minkunet import MinkUNet34C, decode_heads
+    torch.manual_seed(1)
+    coords, feats = _scene(n=4000, G=48, batch=2, cin=3, seed=11, negative=True)
+    model = MinkUNet34C(3, 64).cuda().eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.8, 1.2); m.weight.uniform_(0.8, 1.2); m.bias.normal_(0, 0.05)
+        ME.set_forward_mode("fp32")
+        ref = model(ME.SparseTensor(feats, coords, device="cuda")).F
+    eng = MinkUNetEngine(model)
+    got = eng(coords.cuda(), feats.cuda())
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert got.shape == ref.shape == (len(coords), 64)
+    assert err <= 2e-2 * scale, "engine vs fp32 module path: max err %.3e, scale %.3e" % (err, scale)
+    # head decode kernel == the torch ops of eval_joint.py:173-190 on the same features
+    xyz, sc, cls, prob = eng.decode(got)
+    wxyz, wsc, wcls, wprob = decode_heads(got)
+    assert torch.equal(cls, wcls)
+    torch.testing.assert_close(xyz, wxyz, rtol=0, atol=0)
+    torch.testing.assert_close(sc, wsc, rtol=1e-6, atol=0)
+    torch.testing.assert_close(prob, wprob, rtol=1e-5, atol=1e-7)
+    # second call on another scene re-uses the packed weights
+    coords2, feats2 = _scene(n=1000, G=30, batch=1, cin=3, seed=12)
+    out2 = eng(coords2.cuda(), feats2.cuda())
+    assert out2.shape == (len(coords2), 64) and torch.isfinite(out2).all()

@@ -47,3 +47,32 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
+
+# ---- per-convolution breakdown (CUDA events around every conv_table_forward call)
+import collections  # noqa: E402
+from canonicalvoting_b200.sparse import functional as Fn  # noqa: E402
+rec = []
+orig = Fn.conv_table_forward
+
+
+def timed(x, w, table, bias=None, mode=None):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = orig(x, w, table, bias, mode)
+    b.record()
+    rec.append(((table.shape[0], w.shape[1], w.shape[2], table.shape[1]), a, b))
+    return out
+
+
+Fn.conv_table_forward = timed
+step()
+torch.cuda.synchronize()
+agg = collections.OrderedDict()
+for key, a, b in rec:
+    agg.setdefault(key, []).append(a.elapsed_time(b))
+print("%8s %5s %5s %4s %5s %10s %10s" % ("n_out", "cin", "cout", "k3", "calls", "ms/call", "ms total"))
+tot = 0.0
+for key, v in agg.items():
+    tot += sum(v)
+    print("%8d %5d %5d %4d %5d %10.3f %10.3f" % (key + (len(v), sum(v) / len(v), sum(v))))
+print("total conv ms (incl. weight transposes):", tot)
