@@ -4,17 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one synthetic scene (BASELINE.json configs[1],
-"C2": 50 000 points voting into a 128^3 grid with num_rots = 12).  Prints ONE JSON line
-(rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+One "step" = one pass of the hot path over one synthetic scene: BASELINE.json configs[1] ("C2"): MinkUNet34C
+forward on a 50 000-voxel scan -> head decode -> Hough voting (hv_cuda.forward) into a 128^3 grid with
+num_rots = 12.  Prints ONE JSON line (rank 0).  DESIGN.md "Measurement" defines every field.
 
-  value      scenes/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed, L2 flushed
-             between timed steps, max over ranks
-  e2e        scenes/s through the reference-facing API (`hv_cuda.forward`) starting from pinned HOST
-             buffers: H2D of the scene + geometry sync + vote + D2H of the step's result
-  roofline   the vote op (scatter + write-out kernels): algorithmic bytes 40N + 24G per scene
-              / measured kernel time, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the oracle port (oracle/hv_oracle.c, OpenMP, all host cores) on a bounded sample
+  value        scenes/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed per step, L2 flushed between
+               timed steps, max over ranks
+  e2e          scenes/s through the reference-facing API starting from pinned HOST buffers: H2D of coords + feats ->
+               engine -> decode -> hv_cuda.forward (with its geometry sync) -> D2H of the step's result
+  roofline     the dominant kernel group of the step = the tcgen05 sparse-convolution program of the U-Net:
+               algorithmic FLOPs 2 * sum(pairs * cin * cout) / its CUDA-event time, against the measured dense
+               tensor peak; `vote` holds the HBM roofline of the vote op (40 N + 24 G bytes)
+  cpu_baseline the oracle ports (oracle/sparse_oracle.py FastCpuNet + oracle/hv_oracle.c OpenMP) on the host cores,
+               bounded sample
 """
 import argparse
 import json
@@ -30,6 +32,8 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+NCLASSES = 9
+
 
 # ----------------------------------------------------------------------------- helpers
 def load_peaks():
@@ -37,10 +41,10 @@ def load_peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -88,84 +92,126 @@ def scene_for(workload, seed):
     return synthetic.make_config(workload, seed=seed)
 
 
-def algorithmic_bytes(n, dims):
-    """SURVEY.md 8d contract figure: read every input once (10 floats/point), write every output
-    voxel once (6 floats/voxel)."""
+def vote_bytes(n, dims):
+    """SURVEY.md 8d contract figure: read every input once (10 floats/point), write every output voxel once (6 floats)."""
     return 40 * n + 24 * int(dims[0]) * int(dims[1]) * int(dims[2])
 
 
-# ----------------------------------------------------------------------------- CPU arm
-def cpu_vote_scenes_per_s(workload, max_seconds, threads=None):
-    """The oracle port timed on the host cores: bounded sample of the same workload."""
+def make_model():
+    import torch
+    from canonicalvoting_b200.minkunet import MinkUNet34C
+    torch.manual_seed(0)
+    model = MinkUNet34C(3, 6 * NCLASSES + NCLASSES + 1).eval()       # train_joint.py:218: random init, there is no checkpoint offline
+    with torch.no_grad():                                             # non-trivial BN statistics so that folding is exercised
+        g = torch.Generator().manual_seed(1)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.05, generator=g)
+                m.running_var.uniform_(0.8, 1.2, generator=g)
+    return model
+
+
+def scene_tensors(sc):
+    import torch
+    coords = torch.cat([torch.zeros(len(sc["coords"]), 1, dtype=torch.int32), torch.from_numpy(sc["coords"])], 1).contiguous()
+    feats = (torch.from_numpy(sc["feats"]) * 2.0 - 1.0).contiguous()      # eval_joint.py:168
+    return coords, feats
+
+
+def workload_config(workload, sc):
+    G = sc["grid"]
+    return {"workload": "%s: MinkUNet34C(3,64) forward + head decode + Hough voting (hv_cuda.forward) on one synthetic room "
+                        "scene, N=%d voxels, vote grid %d^3, num_rots=%d" % (workload, len(sc["points"]), G, sc["num_rots"]),
+            "points": len(sc["points"]), "grid": [G, G, G], "num_rots": sc["num_rots"], "res": sc["res"],
+            "weights": "random init (no checkpoint offline), BatchNorm in eval mode",
+            "l2": "flushed between timed steps (256 MiB memset)"}
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle ports)
+def cpu_step_seconds(model, sc, frac=1.0):
+    """One pass of the CPU ports over (a spatial crop holding `frac` of) the scene: U-Net, decode, vote."""
+    import torch
+    from canonicalvoting_b200.minkunet import decode_heads
     from oracle import hv_oracle as O
-    threads = threads or O.num_threads()
-    sc = scene_for(workload, 0)
-    res = np.float32(sc["res"])
-    R = sc["num_rots"]
-    O.forward(sc["points"], sc["xyz"], sc["scale"], sc["obj"], res, R, acc64=False, threads=threads)  # warm
-    t0, n = time.perf_counter(), 0
-    while True:
-        O.forward(sc["points"], sc["xyz"], sc["scale"], sc["obj"], res, R, acc64=False, threads=threads)
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt >= max_seconds or n >= 2000:
-            break
-    return n / dt, threads, "%d x %s scene (N=%d, R=%d) in %.1f s, oracle/hv_oracle.c OpenMP atomics" % (
-        n, workload, len(sc["points"]), R, dt)
+    from oracle import sparse_oracle as SO
+    coords, feats = scene_tensors(sc)
+    pts, R, res = sc["points"], sc["num_rots"], np.float32(sc["res"])
+    if frac < 1.0:   # crop along x: the U-Net cost is linear in the voxel count
+        order = np.argsort(sc["coords"][:, 0], kind="stable")[: max(int(len(pts) * frac), 512)]
+        coords, feats, pts = coords[order], feats[order], pts[order]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        f = SO.FastCpuNet(model).forward(coords, feats)
+        xyz, scale, cls, prob = decode_heads(f, NCLASSES, True)
+    t1 = time.perf_counter()
+    O.forward(pts, xyz.numpy(), scale.numpy(), prob.numpy(), res, R, acc64=False, threads=O.num_threads())
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, t2 - t1, len(pts)
+
+
+def cpu_baseline(model, workload, sc, max_seconds):
+    import torch
+    from oracle import hv_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frac = 0.25
+    t, tu, tv, n = cpu_step_seconds(model, sc, frac)            # calibration pass (also warms the thread pools)
+    frac = float(min(1.0, max(0.05, frac * 0.5 * max_seconds / max(t, 1e-3))))
+    t, tu, tv, n = cpu_step_seconds(model, sc, frac)
+    scenes_per_s = (n / len(sc["points"])) / t
+    return {"value": scenes_per_s, "unit": "scenes/s", "cores": cores, "kind": "port",
+            "sample": "1 pass over a %.0f%% spatial crop of the %s scene (%d voxels) in %.1f s (U-Net %.1f s, vote %.2f s), "
+                      "extrapolated linearly in the voxel count; oracle/sparse_oracle.py FastCpuNet (torch CPU, %d threads) + "
+                      "oracle/hv_oracle.c (OpenMP, %d threads)" % (100 * frac, workload, n, t, tu, tv, cores, O.num_threads())}
 
 
 def run_reference_arm(args):
-    """--impl reference.  The reference has NO CPU implementation (hv_cuda.cpp:26-28 rejects CPU
-    tensors) and its CUDA build cannot run without a GPU process of its own; per the task contract
-    the arm times the oracle PORT of the path on the host cores, all threads."""
+    """--impl reference.  The reference has NO CPU implementation of this path (hv_cuda.cpp:26-28 rejects CPU tensors;
+    MinkowskiEngine is not installable offline), so per the task contract the arm times the oracle PORTS on the host
+    cores, all threads.  Each step processes a spatial crop of the scene sized so that the whole run takes ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = []
-    from oracle import hv_oracle as O
-    threads = O.num_threads()
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     sc = scene_for(args.workload, 0)
-    res, R = np.float32(sc["res"]), sc["num_rots"]
-    reps = {"C1": 200, "C2": 10, "C5": 2}[args.workload]   # scenes per step: bounded sample
+    model = make_model()
+    t, _, _, _ = cpu_step_seconds(model, sc, 0.1)
+    t, _, _, n = cpu_step_seconds(model, sc, 0.1)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    frac = float(min(1.0, max(0.02, 0.1 * budget / max(t, 1e-3))))
+    per_step, n_used = [], 0
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            O.forward(sc["points"], sc["xyz"], sc["scale"], sc["obj"], res, R, acc64=False, threads=threads)
+        t, _, _, n_used = cpu_step_seconds(model, sc, frac)
         if it >= args.warmup:
-            per_step.append((time.perf_counter() - t0) / reps)
-    ms = 1e3 * float(np.mean(per_step))
-    val = 1e3 / ms
+            per_step.append(t)
+    scene_frac = n_used / len(sc["points"])
+    ms_scene = 1e3 * float(np.mean(per_step)) / scene_frac
+    val = 1e3 / ms_scene
+    sample = "each step = a %.0f%% spatial crop (%d voxels) of the scene; scenes/s extrapolated linearly in the voxel count" % (
+        100 * scene_frac, n_used)
     line = {
         "impl": "reference", "metric": "scenes_per_sec", "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_scene, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, sc),
-        "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": threads, "kind": "port",
-                         "sample": "%d scenes per step x %d steps, oracle/hv_oracle.c OpenMP" % (reps, args.steps)},
+        "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workload, sc):
-    G = sc["grid"]
-    return {"workload": "%s: vote op (hv_cuda.forward) on one synthetic room scene, N=%d points, grid %d^3, "
-                        "num_rots=%d; MinkUNet34C forward not yet part of the step" % (
-                            workload, len(sc["points"]), G, sc["num_rots"]),
-            "points": len(sc["points"]), "grid": [G, G, G], "num_rots": sc["num_rots"], "res": sc["res"],
-            "l2": "flushed between timed steps (256 MiB memset)"}
-
-
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C5"])
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 1)
 
@@ -178,6 +224,7 @@ def main():
 
     import hv_cuda
     from canonicalvoting_b200 import hv_cuda as H
+    from canonicalvoting_b200.engine import MinkUNetEngine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,60 +239,80 @@ def main():
     # weak scaling: every rank owns its own scenes (scene i -> rank i mod W); no data-path collective
     sc = scene_for(args.workload, seed=rank)
     n, R, res = len(sc["points"]), sc["num_rots"], sc["res"]
-    host = {k: torch.from_numpy(sc[k]).pin_memory() for k in ("points", "xyz", "scale", "obj")}
-    d = {k: v.to(dev) for k, v in host.items()}
+    model_cpu = make_model()
+    model = make_model().to(dev)
+    engine = MinkUNetEngine(model, NCLASSES, True)
+    coords_h, feats_h = scene_tensors(sc)
+    coords_h, feats_h = coords_h.pin_memory(), feats_h.pin_memory()
+    coords_d, feats_d = coords_h.to(dev), feats_h.to(dev)
     res_t = torch.tensor(res, dtype=torch.float32, device=dev)
     rots_t = torch.tensor(R, dtype=torch.int32, device=dev)
-    corner, _, dims = H.grid_dims(d["points"], res)
+    pts_d = (coords_d[:, 1:].float() * res).contiguous()
+    corner, _, dims = H.grid_dims(pts_d, res)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value, roofline): the step = vote op, async, geometry known
-    def step_resident():
-        return H.forward_host(d["points"], d["xyz"], d["scale"], d["obj"], res, R, corner, dims)
+    # ---- device-resident step: U-Net program -> decode -> vote (grid geometry known on the host, no sync inside)
+    def step_resident(marks=None):
+        if marks is not None:
+            marks[0].record(stream)
+        f = engine(coords_d, feats_d)
+        if marks is not None:
+            marks[1].record(stream)
+        xyz, scale, cls, prob = engine.decode(f)
+        points = (coords_d[:, 1:].float() * res).contiguous()         # eval_joint.py:193
+        if marks is not None:
+            marks[2].record(stream)
+        out = H.forward_host(points, xyz, scale, prob, res, R, corner, dims)
+        if marks is not None:
+            marks[3].record(stream)
+        return out
 
     for _ in range(args.warmup):
         flush.zero_()
         step_resident()
     barrier()
-    evs = []
+    marks = []
     with ClockSampler(local) as clk:
         for _ in range(args.steps):
             flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            out = step_resident()
-            e1.record(stream)
-            evs.append((e0, e1))
+            m = [ev(), ev(), ev(), ev()]
+            out = step_resident(m)
+            marks.append(m)
         barrier()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
+    step_ms = [m[0].elapsed_time(m[3]) for m in marks]
+    unet_ms = [m[0].elapsed_time(m[1]) for m in marks]
+    vote_ms = [m[2].elapsed_time(m[3]) for m in marks]
     t_resident = float(np.sum(step_ms)) / 1e3
     del out
 
     # ---- end to end through the reference-facing API with HOST buffers
     def step_e2e():
-        dd = [host[k].to(dev, non_blocking=True) for k in ("points", "xyz", "scale", "obj")]
-        go, gr, gs = hv_cuda.forward(dd[0], dd[1], dd[2], dd[3], res_t, rots_t)
+        c = coords_h.to(dev, non_blocking=True)
+        f = feats_h.to(dev, non_blocking=True)
+        xyz, scale, cls, prob = engine.predict(c, f)
+        go, gr, gs = hv_cuda.forward((c[:, 1:].float() * res).contiguous(), xyz, scale, prob, res_t, rots_t)
         peak = torch.stack([go.max(), go.argmax().float()])
         return peak.cpu()          # D2H read of the step's result (peak value + voxel)
 
     for _ in range(args.warmup):
         step_e2e()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     e0.record(stream)
     for _ in range(args.steps):
         step_e2e()
     e1.record(stream)
     barrier()
     t_e2e = e0.elapsed_time(e1) / 1e3
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = 8
+    h2d = coords_h.numel() * 4 + feats_h.numel() * 4
+    d2h = 8 + 4 * 4                                    # result + the per-level voxel counts the coordinate manager reads
 
     # ---- max over ranks
     times = torch.tensor([t_resident, t_e2e], dtype=torch.float64, device=dev)
@@ -254,50 +321,71 @@ def main():
     t_resident, t_e2e = times.tolist()
 
     if rank == 0:
-        peak_gbs, peak_src = load_peaks()
-        ms = 1e3 * t_resident / args.steps
-        bytes_alg = algorithmic_bytes(n, dims)
-        kern_ms = float(np.median(step_ms))
-        achieved = bytes_alg / (kern_ms * 1e-3) / 1e9
-        cpu_val, cpu_cores, cpu_sample = cpu_vote_scenes_per_s(args.workload, args.cpu_seconds)
-        cpu = {"value": cpu_val, "unit": "scenes/s", "cores": cpu_cores, "kind": "port", "sample": cpu_sample}
-        # the reference's own CUDA kernel (unmodified, built for sm_100a) on this same GPU, reported beside it
-        try:
+        hbm_gbs, bf16_tf, peak_src = load_peaks()
+        # algorithmic FLOPs of the convolution program: 2 * pairs * cin * cout per op, pairs counted from the tables
+        arr, _, keep = engine.build(coords_d, feats_d)
+        flops = program_flops(engine, keep[0], arr)
+        unet_med = float(np.median(unet_ms))
+        vote_med = float(np.median(vote_ms))
+        tflops = flops / (unet_med * 1e-3) / 1e12
+        tf32_peak = bf16_tf / 2.0
+        vbytes = vote_bytes(n, dims)
+        vote_gbs = vbytes / (vote_med * 1e-3) / 1e9
+        cpu = cpu_baseline(model_cpu, args.workload, sc, args.cpu_seconds)
+        try:   # the reference's own CUDA vote kernel (unmodified, built for sm_100a) on this same GPU, reported beside it
             from oracle import build_ref
             ref = build_ref.load_ref()
             if ref is not None:
+                xyz, scale, cls, prob = engine.predict(coords_d, feats_d)
                 for _ in range(3):
-                    ref.forward(d["points"], d["xyz"], d["scale"], d["obj"], res_t, rots_t)
+                    ref.forward(pts_d, xyz, scale, prob, res_t, rots_t)
                 torch.cuda.synchronize()
-                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = 10
+                r0, r1 = ev(), ev()
                 r0.record(stream)
-                for _ in range(reps):
-                    ref.forward(d["points"], d["xyz"], d["scale"], d["obj"], res_t, rots_t)
+                for _ in range(10):
+                    ref.forward(pts_d, xyz, scale, prob, res_t, rots_t)
                 r1.record(stream)
                 torch.cuda.synchronize()
-                cpu["reference_cuda_same_gpu"] = {"ms_per_scene": r0.elapsed_time(r1) / reps,
-                                                  "what": "unmodified hv_cuda.forward built for sm_100a (oracle/_ref)"}
+                cpu["reference_vote_cuda_same_gpu"] = {"ms_per_scene": r0.elapsed_time(r1) / 10,
+                                                       "what": "unmodified hv_cuda.forward built for sm_100a (oracle/_ref)"}
         except Exception as e:  # pragma: no cover
-            cpu["reference_cuda_same_gpu"] = {"error": repr(e)}
+            cpu["reference_vote_cuda_same_gpu"] = {"error": repr(e)}
         line = {
             "metric": "scenes_per_sec", "value": world * args.steps / t_resident, "unit": "scenes/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, sc),
-            "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                         "kernel": "hv_scatter_kernel + hv_finalize_kernel (whole vote op)",
-                         "algorithmic_bytes": bytes_alg, "kernel_ms": kern_ms},
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (U-Net) / f32 (vote)",
+            "data": "synthetic", "config": workload_config(args.workload, sc),
+            "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": (len(arr) + 16 + 1 + 2) * args.steps,
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
+                         "traffic": None, "peak_source": peak_src + ": bf16 sustained / 2 (kind::tf32 runs at half the bf16 rate)",
+                         "kernel": "sc_conv_tc_kernel program of the U-Net (%d fused conv ops incl. stem and finish passes)" % len(arr),
+                         "algorithmic_flops": flops, "kernel_ms": unet_med,
+                         "vote": {"bound": "hbm", "achieved": vote_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": vote_gbs / hbm_gbs,
+                                  "kernel": "hv_scatter_kernel + hv_finalize_kernel", "algorithmic_bytes": vbytes,
+                                  "kernel_ms": vote_med}},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def program_flops(engine, cm, arr):
+    """2 * sum over ops of (existing (output, offset) pairs) * cin * cout."""
+    import torch
+    seen, total = {}, 0
+    tables = {t.data_ptr(): t for t in cm._nbr.values()}
+    for d in cm._down.values():
+        tables[d["children"].data_ptr()] = d["children"]
+        tables[d["up_table"].data_ptr()] = d["up_table"]
+    for o in arr:
+        t = tables[o.table]
+        if o.table not in seen:
+            seen[o.table] = int((t >= 0).sum())
+        total += 2 * seen[o.table] * o.cin * o.cout
+    return total
 
 
 if __name__ == "__main__":

@@ -131,40 +131,54 @@ sc_conv_tc_kernel(const float *__restrict__ in, int ldi, int cin, const float *_
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = cout, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cout >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
 
-    auto issue_loads = [&](int blk) {
-        const int k = H.act[blk / cblocks], c0 = (blk % cblocks) * kTcKB;
-        unsigned char *st = stage0 + (size_t)(blk % kStages) * stage_bytes;
-        const uint32_t a_s = smem_u32(st), b_s = a_s + a_bytes;
-        const int *idx = s_nbr + k * kTcM;
-        // A: 128 rows x 8 chunks of 16 B; 8 consecutive threads copy one 128-byte row (coalesced, conflict-free)
-        for (int e = tid; e < kTcM * 8; e += kTcThreads) {
-            const int r = e >> 3, c = e & 7;
-            const int src_row = idx[r];
-            const float *src = in + (size_t)(src_row >= 0 ? src_row : 0) * ldi + c0 + c * 4;
-            cp_async16(a_s + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src, src_row >= 0 ? 16u : 0u);
+    // ---- per-thread copy plan: thread (rbase, c) copies the 16-byte chunk c of rows rbase + 32 j of the A tile (4 rows)
+    // and of the B tile (cout / 32 rows) of every k-block; only the source row pointers change, once per kernel offset.
+    const int c = tid & 7, rbase = tid >> 3;
+    uint32_t t_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int r = rbase + 32 * j;
+        t_off[j] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    }
+    const float *a_src[4];
+    uint32_t a_ok[4];
+    const float *b_src = wt;
+    int l_act = 0, l_cb = 0;   // load cursor: (active offset, channel block) of the next k-block to fetch
+    auto setup_offset = [&](int act_i) {
+        const int k = H.act[act_i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = s_nbr[k * kTcM + rbase + 32 * j];
+            a_src[j] = in + (size_t)(idx >= 0 ? idx : 0) * ldi + c * 4;
+            a_ok[j] = idx >= 0 ? 16u : 0u;
         }
-        // B: cout rows (output channels) x 8 chunks: Wt[k][n][c0 .. c0+32)
-        const float *wk = wt + ((size_t)k * cout_total + n0) * cin + c0;
-        for (int e = tid; e < cout * 8; e += kTcThreads) {
-            const int r = e >> 3, c = e & 7;
-            cp_async16(b_s + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), wk + (size_t)r * cin + c * 4, 16u);
+        b_src = wt + ((size_t)k * cout_total + n0 + rbase) * cin + c * 4;
+    };
+    auto issue_loads = [&](int stage) {
+        const uint32_t a_s = smem_u32(stage0 + (size_t)stage * stage_bytes), b_s = a_s + a_bytes;
+        const int coff = l_cb * kTcKB;
+#pragma unroll
+        for (int j = 0; j < 4; j++) cp_async16(a_s + t_off[j], a_src[j] + coff, a_ok[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (rbase + 32 * j < cout) cp_async16(b_s + t_off[j], b_src + (size_t)(32 * j) * cin + coff, 16u);
+        if (++l_cb == cblocks) {
+            l_cb = 0;
+            if (++l_act < H.n_act) setup_offset(l_act);
         }
     };
 
     // ---- main loop: kStages-deep ring of (gathered A tile, weight tile); one thread issues the MMAs
+    if (total > 0) setup_offset(0);
     for (int b = 0; b < kStages - 1; b++) {
         if (b < total) issue_loads(b);
         cp_async_commit();
     }
     for (int it = 0; it < total; it++) {
-        const int pre = it + kStages - 1;
-        if (pre < total) {
-            if (it >= 1) mbar_wait(smem_u32(&H.empty_bar[(it - 1) % kStages]), (uint32_t)(((it - 1) / kStages) & 1));
-            issue_loads(pre);
-        }
-        cp_async_commit();
-        cp_async_wait<kStages - 1>();                                 // block `it` has landed
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        cp_async_wait<kStages - 2>();                                  // this thread's copies of k-block `it` have landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
+        // the stage refilled below was read by the MMAs of k-block it-1: one thread waits for their completion
+        if (tid == 0 && it >= 1) mbar_wait(smem_u32(&H.empty_bar[(it - 1) % kStages]), (uint32_t)(((it - 1) / kStages) & 1));
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -175,6 +189,8 @@ sc_conv_tc_kernel(const float *__restrict__ in, int ldi, int cin, const float *_
                 umma_tf32(tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > 0 || kk > 0) ? 1u : 0u);
             umma_commit(smem_u32(&H.empty_bar[it % kStages]));   // arrives when these MMAs (and all before) have completed
         }
+        if (it + kStages - 1 < total) issue_loads((it + kStages - 1) % kStages);
+        cp_async_commit();
     }
     cp_async_wait<0>();
 

@@ -21,7 +21,6 @@ import torch
 
 from . import _lib
 
-_scalar_cache = {}     # (data_ptr, version, device) -> python scalar
 _work_cache = {}       # (device index, stream id) -> zero-filled workspace tensor
 _dims_work = {}        # device index -> small scratch for the min/max reduction
 
@@ -34,15 +33,18 @@ def _check_input(t, name):
 
 
 def _host_scalar(t):
-    """Value of a 0-dim device tensor (res / num_rots); cached so that the constant
-    tensors HoughVoting holds (train_joint.py:52-53) cost one sync ever, not one per call."""
-    key = (t.data_ptr(), t._version, t.device.index, t.dtype)
-    v = _scalar_cache.get(key)
-    if v is None:
-        if len(_scalar_cache) > 256:
-            _scalar_cache.clear()
-        v = t.item()
-        _scalar_cache[key] = v
+    """Value of a 0-dim device tensor (res / num_rots).  The value is remembered ON THE TENSOR OBJECT (together
+    with its version counter), so the constant tensors HoughVoting holds (train_joint.py:52-53) cost one
+    device->host sync ever, not one per call -- and a new tensor that happens to reuse the address is never
+    mistaken for an old one."""
+    tag = getattr(t, "_cvb200_host_value", None)
+    if tag is not None and tag[0] == t._version:
+        return tag[1]
+    v = t.item()
+    try:
+        t._cvb200_host_value = (t._version, v)
+    except Exception:
+        pass
     return v
 
 

@@ -202,3 +202,24 @@ def test_non_default_stream_and_float64():
     d = hv_cuda.forward(p.double(), x.double(), s.double(), o.double(), res_t, rots_t)
     assert d[0].dtype == torch.float64
     assert_grid_close(d[0].cpu().numpy(), base[0].cpu().numpy(), what="float64 io")
+
+
+def test_scalar_tensors_are_not_confused_by_address_reuse():
+    """res / num_rots arrive as 0-dim device tensors; their host copies are cached per tensor OBJECT."""
+    import hv_cuda
+    sc = small_scene(800, 16, 4, seed=5)
+    p, x, s, o = _dev(sc)
+    res_t = torch.tensor(RES, dtype=torch.float32).cuda()
+    sums = []
+    for R in (4, 8, 4, 12):
+        rots_t = torch.tensor(R, dtype=torch.int32).cuda()      # very likely the same address every time
+        go, _, _ = hv_cuda.forward(p, x, s, o, res_t, rots_t)
+        sums.append(float(go.sum()))
+        del rots_t
+    assert abs(sums[0] - sums[2]) <= 1e-3 * sums[0]
+    assert sums[1] > 1.5 * sums[0] and sums[3] > 2.2 * sums[0]
+    rots_t = torch.tensor(4, dtype=torch.int32).cuda()
+    a = float(hv_cuda.forward(p, x, s, o, res_t, rots_t)[0].sum())
+    rots_t.fill_(8)                                             # in-place update bumps the version counter
+    b = float(hv_cuda.forward(p, x, s, o, res_t, rots_t)[0].sum())
+    assert b > 1.5 * a
