@@ -64,7 +64,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.05)
+            self.stop.wait(0.5)     # nvidia-smi takes driver locks: sample sparsely so that it does not perturb the timed steps
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -279,6 +279,9 @@ def main():
         step_resident()
     barrier()
     marks = []
+    import gc
+    gc.collect()
+    gc.disable()
     with ClockSampler(local) as clk:
         for _ in range(args.steps):
             flush.zero_()
@@ -286,6 +289,7 @@ def main():
             out = step_resident(m)
             marks.append(m)
         barrier()
+    gc.enable()
     step_ms = [m[0].elapsed_time(m[3]) for m in marks]
     unet_ms = [m[0].elapsed_time(m[1]) for m in marks]
     vote_ms = [m[2].elapsed_time(m[3]) for m in marks]
@@ -353,6 +357,7 @@ def main():
         line = {
             "metric": "scenes_per_sec", "value": world * args.steps / t_resident, "unit": "scenes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps,
+            "step_ms": {"median": float(np.median(step_ms)), "min": float(np.min(step_ms)), "max": float(np.max(step_ms))},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (U-Net) / f32 (vote)",
             "data": "synthetic", "config": workload_config(args.workload, sc),
             "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -30,7 +30,7 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class BpParams(ctypes.Structure):
@@ -55,7 +55,8 @@ SIGNATURES.update({
     "cvb200_sc_down_finish": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvb200_sc_kernel_map": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "cvb200_sc_conv_forward": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
-    "cvb200_sc_conv_forward_tc": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
+    "cvb200_sc_conv_forward_tc": (ctypes.c_int, [_f, _i64, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
+    "cvb200_sc_set_conv_impl": (ctypes.c_int, [_i32]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
 })
 
@@ -64,7 +65,7 @@ SIGNATURES.update({
 class ScOp(ctypes.Structure):
     """cvb200_sc_op (include/cvb200.h)."""
     _fields_ = [("kind", _i32), ("cin", _i32), ("cout", _i32), ("k3", _i32), ("ldi", _i32), ("ldo", _i32), ("ldr", _i32),
-                ("relu", _i32), ("n_out", _i64), ("in_", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("table", _vp),
+                ("relu", _i32), ("n_out", _i64), ("n_in", _i64), ("in_", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("table", _vp),
                 ("out", _vp)]
 
 

@@ -266,8 +266,25 @@ __global__ void sc_finish_kernel(float *__restrict__ out, int ldo, int n, int co
 }
 
 // out[o, 0:cout) (row stride ldo) = [relu]( sum_k in[nbr[o,k], 0:cin) (row stride ldi) @ Wt[k]^T + bias + residual )
-int launch_conv_tc(const float *d_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out, int k3,
-                   const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream) {
+int launch_finish(float *d_out, int ldo, int64_t n_out, int cout, const float *d_bias, const float *d_res, int ldr, int relu,
+                  cudaStream_t stream) {
+    const long long total = (long long)n_out * (cout / 4);
+    sc_finish_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(d_out, ldo, (int)n_out, cout, d_bias, d_res, ldr, relu);
+    CVB_LAUNCH_CHECK("sc_finish_kernel");
+    return 0;
+}
+
+int launch_conv_tma(int gather_a, const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
+                    int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
+                    cudaStream_t stream);
+// 2: warp-specialised kernel, A by cp.async producers + B by TMA (sparse_conv_tma.cu); 1: same kernel, A by TMA gather4;
+// 0: cp.async kernel with a CTA-wide barrier per k-block (this file)
+int g_conv_impl = 2;
+
+int launch_conv_tc(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out,
+                   int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream) {
+    if (g_conv_impl != 0)
+        return launch_conv_tma(g_conv_impl == 1, d_in, n_in, ldi, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, d_res, ldr, relu, d_out, ldo, stream);
     CVB_REQUIRE(cin > 0 && cin % kTcKB == 0 && cout >= 16 && cout <= 256 && cout % 16 == 0 && k3 > 0 && k3 <= kTcMaxK3,
                 CVB200_EINVAL, "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout <= 256, K^3 <= %d (got %d, %d, %d)",
                 kTcMaxK3, cin, cout, k3);
@@ -315,18 +332,21 @@ int launch_conv_tc(const float *d_in, int ldi, int cin, const float *d_wt, int c
                                                                  k_relu, d_out, ldo, tmem_cols, nc);
     }
     CVB_LAUNCH_CHECK("sc_conv_tc_kernel");
-    if (split && (d_bias || d_res || relu)) {
-        const long long total = (long long)n_out * (cout / 4);
-        sc_finish_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(d_out, ldo, (int)n_out, cout, d_bias, d_res, ldr, relu);
-        CVB_LAUNCH_CHECK("sc_finish_kernel");
-    }
+    if (split && (d_bias || d_res || relu)) return launch_finish(d_out, ldo, n_out, cout, d_bias, d_res, ldr, relu, stream);
     return 0;
 }
 }  // namespace cvb200
 
 using namespace cvb200;
 
-extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
-                                         int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream_) {
-    return launch_conv_tc(d_in, cin, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, nullptr, 0, 0, d_out, cout, (cudaStream_t)stream_);
+extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_t cin, const float *d_wt, int32_t cout,
+                                         const int32_t *d_nbr, int64_t n_out, int32_t k3, const float *d_bias, float *d_out,
+                                         void *stream_) {
+    return launch_conv_tc(d_in, n_in, cin, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, nullptr, 0, 0, d_out, cout, (cudaStream_t)stream_);
+}
+
+extern "C" int cvb200_sc_set_conv_impl(int32_t impl) {
+    CVB_REQUIRE(impl >= 0 && impl <= 2, CVB200_EINVAL, "sc_set_conv_impl: 0 (cp.async), 1 (TMA gather4) or 2 (cp.async A + TMA B)");
+    g_conv_impl = impl;
+    return 0;
 }

@@ -11,8 +11,8 @@
 
 namespace cvb200 {
 
-int launch_conv_tc(const float *d_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out, int k3,
-                   const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream);
+int launch_conv_tc(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out,
+                   int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream);
 
 // Convolution with a tiny input width (the 3-channel 5^3 stem, utils/minkunet.py:53): one warp per output row, the
 // whole kernel (K^3 x cin x cout) in shared memory, lanes = output channels; neighbour ids are read 32 at a time and
@@ -96,7 +96,7 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
     for (int i = 0; i < n_ops; i++) {
         const cvb200_sc_op &o = ops[i];
         if (o.kind == CVB200_OP_CONV_TC) {
-            const int rc = launch_conv_tc(o.in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr, o.relu,
+            const int rc = launch_conv_tc(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr, o.relu,
                                           o.out, o.ldo, stream);
             if (rc) return rc;
         } else if (o.kind == CVB200_OP_CONV_SMALLCIN) {

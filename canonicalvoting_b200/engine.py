@@ -108,6 +108,7 @@ class MinkUNetEngine:
         o.kind, o.cin, o.cout, o.k3 = kind, cin, cout, k3
         o.ldi, o.ldo, o.ldr, o.relu = src.ld, dst.ld, residual.ld if residual is not None else 0, 1 if relu else 0
         o.n_out = table.shape[0]
+        o.n_in = src.buf.shape[0]
         o.in_, o.w, o.bias = src.ptr, w.data_ptr(), b.data_ptr() if b is not None else None
         o.residual = residual.ptr if residual is not None else None
         o.table, o.out = table.data_ptr(), dst.ptr

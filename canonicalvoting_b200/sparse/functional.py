@@ -47,7 +47,7 @@ def conv_table_forward(x, w, table, bias=None, mode=None):
     with torch.cuda.device(x.device):
         if mode == "tf32" and cin % 32 == 0 and cout % 16 == 0 and 16 <= cout <= 256 and k3 <= 32:
             wt = w.transpose(1, 2).contiguous()     # [k3, cout, cin]: K-major B operand
-            rc = L.cvb200_sc_conv_forward_tc(_ptr(x), cin, _ptr(wt), cout, _ptr(table), n_out, k3,
+            rc = L.cvb200_sc_conv_forward_tc(_ptr(x), x.shape[0], cin, _ptr(wt), cout, _ptr(table), n_out, k3,
                                              _ptr(b) if b is not None else None, _ptr(out), _stream())
             _lib.check(rc, "cvb200_sc_conv_forward_tc")
         else:

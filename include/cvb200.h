@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 7
+#define CVB200_ABI_VERSION 8
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -174,9 +174,14 @@ int cvb200_sc_conv_forward(const float *d_in, int32_t cin, const float *d_w, int
 
 /* Same contraction on the tcgen05 tensor cores (kind::tf32, fp32 accumulation in tensor memory):
  * d_wt is the weight PRE-TRANSPOSED to [k3, cout, cin].  Requires cin % 32 == 0, cout % 16 == 0,
- * 16 <= cout <= 256, k3 <= 32 and 16-byte aligned pointers. */
-int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
+ * 16 <= cout <= 256, k3 <= 32 and 16-byte aligned pointers; n_in = rows of d_in. */
+int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
                               int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
+
+/* Operand movement of the tensor-core convolution (all build the same tiles; selectable for A/B measurements):
+ * 2 = warp-specialised kernel, neighbour rows by cp.async producer warps + weight block by TMA (default);
+ * 1 = same kernel, neighbour rows by TMA tile::gather4;  0 = cp.async kernel with one CTA barrier per k-block. */
+int cvb200_sc_set_conv_impl(int32_t impl);
 
 /* One fused convolution of an inference program (cvb200_sc_run_program):
  *   out[:, 0:cout) (row stride ldo) = [relu]( sum_k in[table[o,k], 0:cin) (row stride ldi) @ W[k] + bias + residual )
@@ -189,7 +194,7 @@ int cvb200_sc_conv_forward_tc(const float *d_in, int32_t cin, const float *d_wt,
 typedef struct cvb200_sc_op {
     int32_t kind, cin, cout, k3;
     int32_t ldi, ldo, ldr, relu;
-    int64_t n_out;
+    int64_t n_out, n_in;     /* rows of the output / of the input feature matrix */
     const float *in;
     const float *w;
     const float *bias;       /* [cout] or NULL */

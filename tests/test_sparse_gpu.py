@@ -219,3 +219,27 @@ def test_engine_matches_module_path_and_oracle():
     coords2, feats2 = _scene(n=1000, G=30, batch=1, cin=3, seed=12)
     out2 = eng(coords2.cuda(), feats2.cuda())
     assert out2.shape == (len(coords2), 64) and torch.isfinite(out2).all()
+
+
+def test_tma_gather4_conv_equals_cp_async_conv():
+    """The TMA-fed warp-specialised kernel (tile::gather4 for the neighbour rows, -1 = out-of-bounds = zero fill)
+    builds the same shared-memory tiles as the cp.async kernel: results agree to float-atomic ordering."""
+    from canonicalvoting_b200 import _lib
+    from canonicalvoting_b200.sparse.functional import conv_table_forward
+    L = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    try:
+        for (n_in, n_out, cin, cout, k3) in [(500, 130, 64, 32, 27), (3000, 3000, 96, 96, 27), (900, 200, 256, 256, 27),
+                                             (4000, 1000, 128, 96, 8), (700, 700, 96, 64, 1)]:
+            table = torch.randint(-1, n_in, (n_out, k3), generator=g, dtype=torch.int64).int()
+            table[torch.rand(n_out, k3, generator=g) < 0.5] = -1
+            x = torch.randn(n_in, cin, generator=g).cuda()
+            w = torch.randn(k3, cin, cout, generator=g).cuda() * 0.1
+            L.cvb200_sc_set_conv_impl(0)
+            ref = conv_table_forward(x, w, table.cuda(), None, mode="tf32")
+            for impl in (1, 2):      # 1: A by TMA gather4; 2 (default): A by cp.async producer warps, B by TMA
+                L.cvb200_sc_set_conv_impl(impl)
+                got = conv_table_forward(x, w, table.cuda(), None, mode="tf32")
+                assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), (impl, n_in, n_out, cin, cout, k3)
+    finally:
+        L.cvb200_sc_set_conv_impl(2)
