@@ -17,6 +17,7 @@ compat package) into a flat program of fused convolution ops executed back to ba
     feats = engine(coords_int32_cuda, feats_cuda)      # == model(ME.SparseTensor(feats, coords)).F up to TF32 rounding
     xyz, scale, class_pred, prob = engine.predict(coords, feats)
 """
+import collections
 import ctypes
 
 import torch
@@ -64,13 +65,26 @@ class _Slice:
 
 
 class MinkUNetEngine:
-    def __init__(self, model, nclasses=9, log_scale=True):
-        self.nclasses, self.log_scale = nclasses, log_scale
+    def __init__(self, model, nclasses=9, log_scale=True, pipeline=False):
+        """pipeline=True builds the coordinate maps of a scene on a side stream: their (few) host synchronisations
+        then wait only for the map kernels, not for the previous scene's convolutions still running on the caller's
+        stream, so consecutive scenes overlap.  The caller must then hand in inputs that are already complete
+        (e.g. produced by `upload`), because the side stream does not wait for the caller's stream."""
+        self.nclasses, self.log_scale, self.pipeline = nclasses, log_scale, pipeline
         self.model = model
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("MinkUNetEngine needs the model on a CUDA device (no CPU path)")
+        self._side = torch.cuda.Stream(self.device) if pipeline else None
+        self._ring = collections.deque()      # (tensors used by launches in flight, completion event)
         self.refresh()
+
+    def upload(self, coords_host, feats_host):
+        """Host (ideally pinned) -> device copies on the engine's map stream; returns device tensors ready for __call__."""
+        if self._side is None:
+            return coords_host.to(self.device, non_blocking=True), feats_host.to(self.device, non_blocking=True)
+        with torch.cuda.stream(self._side):
+            return coords_host.to(self.device, non_blocking=True), feats_host.to(self.device, non_blocking=True)
 
     def refresh(self):
         """(Re)pack the model's parameters: call again after the weights changed."""
@@ -146,18 +160,27 @@ class MinkUNetEngine:
             cm._nbr[key] = t
         return t
 
-    def build(self, coords, feats):
-        """Coordinate maps + buffers + program for one batch of scenes. Returns (ops array, output slice, keep-alive list)."""
+    def build_maps(self, coords):
+        """Coordinate levels + every neighbour table the network needs (device work + one scalar read per level)."""
         cm = CoordinateManager(coords)
+        for ts in (1, 2, 4, 8):
+            cm.down(ts)
+        cm.kernel_map(1, self.model.conv0p1s1.kernel_size)
+        for ts in (1, 2, 4, 8, 16):
+            cm.kernel_map(ts, 3)
+            self._identity(cm, ts)
+        return cm
+
+    def build(self, coords, feats, cm=None):
+        """Buffers + program for one batch of scenes. Returns (ops array, output slice, keep-alive list)."""
+        if cm is None:
+            cm = self.build_maps(coords)
         dev, f32 = self.device, torch.float32
         ts_list = [1, 2, 4, 8, 16]
-        for ts in ts_list[:-1]:
-            cm.down(ts)
         n = {ts: cm.levels[ts].n for ts in ts_list}
         P = self.planes
         ops, keep = [], [cm, feats]
         # concat buffers of the decoder: [transposed-conv output | encoder skip]
-        dec_planes = {8: P["block5"][0], 4: P["block6"][0], 2: P["block7"][0], 1: P["block8"][0]}
         tr_out = {8: self.w["convtr4p16s2"][0].shape[1], 4: self.w["convtr5p8s2"][0].shape[1],
                   2: self.w["convtr6p4s2"][0].shape[1], 1: self.w["convtr7p2s2"][0].shape[1]}
         skip_c = {8: P["block3"][0], 4: P["block2"][0], 2: P["block1"][0], 1: self.init_dim}
@@ -193,10 +216,24 @@ class MinkUNetEngine:
             raise RuntimeError("MinkUNetEngine: CUDA tensors expected (there is no CPU path)")
         L = _lib.load()
         with torch.cuda.device(self.device):
-            arr, out, keep = self.build(coords.to(torch.int32).contiguous(), feats.float())
+            main = torch.cuda.current_stream()
+            coords = coords.to(torch.int32).contiguous()
+            if self._side is not None:
+                with torch.cuda.stream(self._side):
+                    cm = self.build_maps(coords)
+                    ready = self._side.record_event()
+                main.wait_event(ready)
+            else:
+                cm = self.build_maps(coords)
+            arr, out, keep = self.build(coords, feats.float(), cm)
             rc = L.cvb200_sc_run_program(arr, len(arr), _stream())
             _lib.check(rc, "cvb200_sc_run_program")
-        self._keep = keep      # buffers must outlive the asynchronous launches
+            # everything the asynchronous launches touch stays alive until they are known to have completed
+            self._ring.append((keep, main.record_event()))
+            while len(self._ring) > 3:
+                old_keep, done = self._ring.popleft()
+                done.synchronize()
+                del old_keep
         return out.buf
 
     def decode(self, feats):

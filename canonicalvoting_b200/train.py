@@ -1,0 +1,58 @@
+"""Training step of the joint model (train_joint.py:244-288) on canonicalvoting_b200.sparse, data-parallel over scenes.
+
+The reference trains on one GPU (`model.cuda()`, train_joint.py:230).  Here scenes shard across ranks (one process
+per GPU): every rank builds ONE sparse tensor from its own scenes (batch index = coordinate column 0, exactly like
+`ME.utils.batched_coordinates`, train_joint.py:82), runs forward / losses / backward locally, and gradients are
+averaged with NCCL all-reduce (torch DistributedDataParallel buckets, overlapped with the backward pass).  BatchNorm
+statistics stay per rank (the reference's BN also sees only its own 3-scene batch; SyncBN would change semantics).
+Masked-mean losses make "mean of per-rank means" differ slightly from a global mean when object-point counts differ
+between ranks -- the usual DDP semantics.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import sparse as ME
+
+NCLASSES = 9
+
+
+def collate(scenes):
+    """List of synthetic scenes (canonicalvoting_b200.synthetic) -> the 6-tuple of train_joint.py's collate_fn (:78-90)."""
+    coords = ME.utils.batched_coordinates([torch.from_numpy(s["coords"]) for s in scenes])
+    cat = lambda k, dt: torch.cat([torch.from_numpy(s[k]) for s in scenes]).to(dt)
+    return (coords, cat("feats", torch.float32), cat("xyz_labels", torch.float32), cat("scale_labels", torch.float32),
+            cat("class_labels", torch.int64))
+
+
+def joint_loss(out_f, xyz_labels, scale_labels, class_labels, log_scale=True, xyz_factor=1.0, scale_factor=1.0):
+    """train_joint.py:253-283: per-class xyz / scale heads gathered by the GT class, masked MSE x2 + 10-way CE."""
+    nc = NCLASSES
+    idx = class_labels.clone()
+    idx[(idx < 0) | (idx == nc)] = 0
+    idx = idx.view(-1, 1, 1).expand(-1, 1, 3)
+    xyz = torch.gather(out_f[:, :3 * nc].reshape(-1, nc, 3), 1, idx)[:, 0]
+    scale = torch.gather(out_f[:, 3 * nc:6 * nc].reshape(-1, nc, 3), 1, idx)[:, 0]
+    logits = out_f[:, 6 * nc:]
+    mask = (class_labels < nc) & (class_labels >= 0)
+    loss = F.cross_entropy(logits, class_labels)
+    if bool(mask.any()):
+        tgt = torch.log(scale_labels[mask]) if log_scale else scale_labels[mask]
+        loss = loss + scale_factor * torch.mean((scale[mask] - tgt) ** 2) + xyz_factor * torch.mean((xyz[mask] - xyz_labels[mask]) ** 2)
+    return loss
+
+
+def train_step(model, optimizer, batch, device):
+    """One optimisation step on this rank's batch; `model` may be wrapped in DistributedDataParallel."""
+    coords, feats, xyz_l, scale_l, class_l = batch
+    feats = feats * 2.0 - 1.0                                                  # train_joint.py:248-249
+    optimizer.zero_grad(set_to_none=True)
+    out = model(ME.SparseTensor(feats.to(device), coords.to(device), device=device))
+    loss = joint_loss(out.F, xyz_l.to(device), scale_l.to(device), class_l.to(device))
+    loss.backward()
+    optimizer.step()
+    return loss.detach()
+
+
+def shard_scenes(n_scenes, rank, world):
+    """Scene i -> rank i mod world."""
+    return [i for i in range(n_scenes) if i % world == rank]
