@@ -47,21 +47,43 @@ def _fold(conv, bn):
 
 
 class _Slice:
-    """Column slice [c0, c0+c) of a row-major float32 buffer [n, ld]."""
+    """Column slice [c0, c0+c) of a row-major float32 matrix [rows, ld] that lives at byte address `base`."""
+    __slots__ = ("base", "rows", "ld", "c0", "c")
 
-    def __init__(self, buf, c0, c):
-        self.buf, self.c0, self.c = buf, c0, c
+    def __init__(self, base, rows, ld, c0, c):
+        self.base, self.rows, self.ld, self.c0, self.c = base, rows, ld, c0, c
 
     @property
     def ptr(self):
-        return self.buf.data_ptr() + 4 * self.c0
+        return self.base + 4 * self.c0
 
-    @property
-    def ld(self):
-        return self.buf.shape[1]
+    def cols(self, c0, c):
+        return _Slice(self.base, self.rows, self.ld, self.c0 + c0, c)
 
-    def tensor(self):
-        return self.buf[:, self.c0:self.c0 + self.c]
+
+class _Arena:
+    """One allocation per forward pass for every activation buffer of the program (sizes are known once the
+    coordinate levels are): matrices are carved out at 256-byte aligned offsets."""
+
+    def __init__(self, device):
+        self.device, self.items, self.total = device, [], 0
+
+    def matrix(self, rows, cols):
+        sl = _Slice(self.total, rows, cols, 0, cols)        # base = offset for now, rebased in commit()
+        self.items.append(sl)
+        self.total += (rows * cols * 4 + 255) // 256 * 256
+        return sl
+
+    def commit(self):
+        self.buf = torch.empty(max(self.total, 256), dtype=torch.uint8, device=self.device)
+        base = self.buf.data_ptr()
+        for sl in self.items:
+            sl.base += base
+        return self.buf
+
+    def tensor(self, sl):
+        off = sl.base - self.buf.data_ptr()
+        return self.buf[off:off + sl.rows * sl.ld * 4].view(torch.float32).view(sl.rows, sl.ld)
 
 
 class MinkUNetEngine:
@@ -114,6 +136,8 @@ class MinkUNetEngine:
 
     # ------------------------------------------------------------------ program construction
     def _op(self, ops, name, src, dst, table, relu, residual=None):
+        """Append one fused convolution; slice base addresses are arena offsets until the arena is committed, so the
+        pointer fields are filled in by build() afterwards (ops keep references to their slices)."""
         w, b, kind = self.w[name]
         k3 = w.shape[0]
         cin, cout = (w.shape[2], w.shape[1]) if kind == 0 else (w.shape[1], w.shape[2])
@@ -122,32 +146,24 @@ class MinkUNetEngine:
         o.kind, o.cin, o.cout, o.k3 = kind, cin, cout, k3
         o.ldi, o.ldo, o.ldr, o.relu = src.ld, dst.ld, residual.ld if residual is not None else 0, 1 if relu else 0
         o.n_out = table.shape[0]
-        o.n_in = src.buf.shape[0]
-        o.in_, o.w, o.bias = src.ptr, w.data_ptr(), b.data_ptr() if b is not None else None
-        o.residual = residual.ptr if residual is not None else None
-        o.table, o.out = table.data_ptr(), dst.ptr
-        ops.append(o)
+        o.n_in = src.rows
+        o.w, o.bias, o.table = w.data_ptr(), b.data_ptr() if b is not None else None, table.data_ptr()
+        ops.append((o, src, dst, residual))
 
-    def _blocks(self, ops, keep, block, cm, ts, x, out_slice=None):
+    def _blocks(self, ops, arena, block, cm, ts, x, out_slice=None):
         """BasicBlocks of one stage; the last block writes into `out_slice` (a skip slot) when given."""
         planes, nblk = self.planes[block]
         n = cm.levels[ts].n
         nbr = cm.kernel_map(ts, 3)
         ident = self._identity(cm, ts)
         for i in range(nblk):
-            t1 = _Slice(torch.empty((n, planes), dtype=torch.float32, device=self.device), 0, planes)
-            keep.append(t1.buf)
+            t1 = arena.matrix(n, planes)
             self._op(ops, "%s.%d.conv1" % (block, i), x, t1, nbr, relu=True)
             res = x
             if ("%s.%d.down" % (block, i)) in self.w:
-                res = _Slice(torch.empty((n, planes), dtype=torch.float32, device=self.device), 0, planes)
-                keep.append(res.buf)
+                res = arena.matrix(n, planes)
                 self._op(ops, "%s.%d.down" % (block, i), x, res, ident, relu=False)
-            if i == nblk - 1 and out_slice is not None:
-                dst = out_slice
-            else:
-                dst = _Slice(torch.empty((n, planes), dtype=torch.float32, device=self.device), 0, planes)
-                keep.append(dst.buf)
+            dst = out_slice if (i == nblk - 1 and out_slice is not None) else arena.matrix(n, planes)
             self._op(ops, "%s.%d.conv2" % (block, i), t1, dst, nbr, relu=True, residual=res)
             x = dst
         return x
@@ -172,42 +188,47 @@ class MinkUNetEngine:
         return cm
 
     def build(self, coords, feats, cm=None):
-        """Buffers + program for one batch of scenes. Returns (ops array, output slice, keep-alive list)."""
+        """Buffers + program for one batch of scenes. Returns (ops array, output tensor [N, Cout], keep-alive list)."""
         if cm is None:
             cm = self.build_maps(coords)
-        dev, f32 = self.device, torch.float32
         ts_list = [1, 2, 4, 8, 16]
         n = {ts: cm.levels[ts].n for ts in ts_list}
         P = self.planes
-        ops, keep = [], [cm, feats]
+        arena, ops = _Arena(self.device), []
+        feats = feats.contiguous()
         # concat buffers of the decoder: [transposed-conv output | encoder skip]
         tr_out = {8: self.w["convtr4p16s2"][0].shape[1], 4: self.w["convtr5p8s2"][0].shape[1],
                   2: self.w["convtr6p4s2"][0].shape[1], 1: self.w["convtr7p2s2"][0].shape[1]}
         skip_c = {8: P["block3"][0], 4: P["block2"][0], 2: P["block1"][0], 1: self.init_dim}
-        cat = {ts: torch.empty((n[ts], tr_out[ts] + skip_c[ts]), dtype=f32, device=dev) for ts in (1, 2, 4, 8)}
-        keep += list(cat.values())
-        skip = {ts: _Slice(cat[ts], tr_out[ts], skip_c[ts]) for ts in cat}
+        cat = {ts: arena.matrix(n[ts], tr_out[ts] + skip_c[ts]) for ts in (1, 2, 4, 8)}
+        skip = {ts: cat[ts].cols(tr_out[ts], skip_c[ts]) for ts in cat}
+        arena.items += list(skip.values())
         # stem: conv0 (5^3, stride 1) + bn0 + relu -> skip slot of level 1
-        src = _Slice(feats.contiguous(), 0, feats.shape[1])
+        src = _Slice(feats.data_ptr(), feats.shape[0], feats.shape[1], 0, feats.shape[1])
         self._op(ops, "conv0p1s1", src, skip[1], cm.kernel_map(1, self.model.conv0p1s1.kernel_size), relu=True)
         x, ts = skip[1], 1
         for (conv, bn, block), skip_ts in zip(_ENCODER, (2, 4, 8, None)):
             d = cm.down(ts)
-            cout = self.w[conv][0].shape[1]
-            y = _Slice(torch.empty((n[2 * ts], cout), dtype=f32, device=dev), 0, cout)
-            keep.append(y.buf)
+            y = arena.matrix(n[2 * ts], self.w[conv][0].shape[1])
             self._op(ops, conv, x, y, d["children"], relu=True)
             ts *= 2
-            x = self._blocks(ops, keep, block, cm, ts, y, skip[skip_ts] if skip_ts is not None else None)
+            x = self._blocks(ops, arena, block, cm, ts, y, skip[skip_ts] if skip_ts is not None else None)
         for (conv, bn, block), fine in zip(_DECODER, (8, 4, 2, 1)):
             d = cm._down[fine]
-            self._op(ops, conv, x, _Slice(cat[fine], 0, tr_out[fine]), d["up_table"], relu=True)
+            up = cat[fine].cols(0, tr_out[fine])
+            arena.items.append(up)
+            self._op(ops, conv, x, up, d["up_table"], relu=True)
             ts = fine
-            x = self._blocks(ops, keep, block, cm, ts, _Slice(cat[fine], 0, cat[fine].shape[1]))
-        out = _Slice(torch.empty((n[1], self.out_channels), dtype=f32, device=dev), 0, self.out_channels)
+            x = self._blocks(ops, arena, block, cm, ts, cat[fine])
+        out = arena.matrix(n[1], self.out_channels)
         self._op(ops, "final", x, out, self._identity(cm, 1), relu=False)
-        arr = (_lib.ScOp * len(ops))(*ops)
-        return arr, out, keep
+        buf = arena.commit()
+        arr = (_lib.ScOp * len(ops))()
+        for i, (o, src_, dst_, res_) in enumerate(ops):
+            o.in_, o.out = src_.ptr, dst_.ptr
+            o.residual = res_.ptr if res_ is not None else None
+            arr[i] = o
+        return arr, arena.tensor(out), [cm, feats, buf]
 
     # ------------------------------------------------------------------ execution
     def __call__(self, coords, feats):
@@ -234,7 +255,7 @@ class MinkUNetEngine:
                 old_keep, done = self._ring.popleft()
                 done.synchronize()
                 del old_keep
-        return out.buf
+        return out
 
     def decode(self, feats):
         """Head decode (eval_joint.py:173-190): features [N, 7*C+1] -> (xyz_pred, scale_pred, class_pred int64, prob_pred)."""

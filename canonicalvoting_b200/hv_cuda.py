@@ -49,7 +49,7 @@ def _host_scalar(t):
 
 
 def _stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _ptr(t):
@@ -82,7 +82,7 @@ def _workspace(L, dims, device):
     """Zero-filled ONCE per (device, stream); cvb200_hv_forward leaves it all-zero again
     (include/cvb200.h contract), so a larger workspace is reused for smaller grids."""
     need = L.cvb200_hv_forward_work_bytes(_lib.i3(dims))
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index))
     w = _work_cache.get(key)
     if w is None or w.numel() < need:
         w = torch.zeros(need, dtype=torch.uint8, device=device)

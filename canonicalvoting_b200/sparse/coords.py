@@ -21,7 +21,9 @@ def _ptr(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of torch's current stream on the current device (the private getter is ~40x cheaper than building a
+    torch.cuda.Stream object, and this is called for every launch)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 class Level:
