@@ -173,8 +173,8 @@ __device__ __forceinline__ void avg_voxel(const float4 a, const float4 b, float 
 constexpr int kFinalizeThreads = 256;
 constexpr int kVoxPerThread = 4;
 
-// One thread = 4 consecutive voxels: 8 x 16-byte workspace loads, 8 x 16-byte zero stores (the workspace is
-// left all-zero for the next call) and 6 x 16-byte streaming output stores.
+// One thread = 4 consecutive voxels: 8 x 16-byte workspace loads, zero stores to the touched sectors only (the
+// workspace is left all-zero for the next call) and 6 x 16-byte streaming output stores.
 __global__ void __launch_bounds__(kFinalizeThreads)
 hv_finalize_kernel(float4 *__restrict__ work, int64_t G, float *__restrict__ grid_obj, float *__restrict__ grid_rot,
                    float *__restrict__ grid_scale) {
@@ -194,8 +194,13 @@ hv_finalize_kernel(float4 *__restrict__ work, int64_t G, float *__restrict__ gri
 #pragma unroll
     for (int j = 0; j < 4; j++)
         if (j < nv) {
-            work[2 * (v + j)] = zero;
-            work[2 * (v + j) + 1] = zero;
+            // re-zero only the sectors a vote touched (a voxel = one 32-byte sector): untouched ones are already zero,
+            // which saves ~3/4 of the zeroing traffic on typical scenes
+            const bool touched = a[j].x != 0.f || a[j].y != 0.f || a[j].z != 0.f || a[j].w != 0.f || b[j].x != 0.f || b[j].y != 0.f;
+            if (touched) {
+                work[2 * (v + j)] = zero;
+                work[2 * (v + j) + 1] = zero;
+            }
             o4[j] = a[j].x;
             avg_voxel(a[j], b[j], r8[2 * j], r8[2 * j + 1], s12[3 * j], s12[3 * j + 1], s12[3 * j + 2]);
         }

@@ -57,6 +57,20 @@ sc_conv_smallcin_kernel(const float *__restrict__ in, int ldi, int cin, const fl
     }
 }
 
+// im2col of a small-width input: col[o, k*cin + c] = in[nbr[o,k], c] (0 where the neighbour is missing; the columns
+// beyond K^3*cin up to ldo are zero padding).  One thread per (row, offset): a warp writes 32*cin consecutive floats.
+// With it the 3-channel 5^3 stem (375 -> 384 columns) becomes a plain [N,384] x [384,32] product on the tensor cores.
+__global__ void sc_im2col_kernel(const float *__restrict__ in, int ldi, int cin, const int *__restrict__ nbr, int n_out, int k3,
+                                 float *__restrict__ col, int ldo) {
+    const int kslots = ldo / cin;                     // >= k3; slots k3..kslots-1 are padding
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_out * kslots) return;
+    const int o = (int)(t / kslots), k = (int)(t - (long long)o * kslots);
+    const int idx = k < k3 ? __ldg(nbr + (size_t)o * k3 + k) : -1;
+    float *dst = col + (size_t)o * ldo + k * cin;
+    for (int c = 0; c < cin; c++) dst[c] = idx >= 0 ? __ldg(in + (size_t)idx * ldi + c) : 0.f;
+}
+
 // Head decode of the joint model (eval_joint.py:173-190): one thread per point.
 //   feats [n, 6*C + C + 1]: xyz[C][3] | scale[C][3] | class logits [C+1] (last = background)
 __global__ void head_decode_kernel(const float *__restrict__ f, int ld, int n, int nclasses, int log_scale,
@@ -114,6 +128,15 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
                 sc_conv_smallcin_kernel<<<blocks, kStemThreads, smem, stream>>>(o.in, o.ldi, o.cin, o.w, o.cout, o.table, (int)o.n_out,
                                                                                o.k3, o.bias, o.relu, o.out, o.ldo);
                 CVB_LAUNCH_CHECK("sc_conv_smallcin_kernel");
+            }
+        } else if (o.kind == CVB200_OP_IM2COL) {
+            CVB_REQUIRE(o.cin >= 1 && o.cin <= 8 && o.ldo % o.cin == 0 && o.ldo >= o.k3 * o.cin && o.in && o.out && o.table, CVB200_EINVAL,
+                        "sc_run_program: op %d: im2col needs cin <= 8 and ldo a multiple of cin covering K^3*cin", i);
+            if (o.n_out > 0) {
+                const long long total = (long long)o.n_out * (o.ldo / o.cin);
+                sc_im2col_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(o.in, o.ldi, o.cin, o.table, (int)o.n_out, o.k3, o.out,
+                                                                                   o.ldo);
+                CVB_LAUNCH_CHECK("sc_im2col_kernel");
             }
         } else {
             CVB_REQUIRE(false, CVB200_EINVAL, "sc_run_program: op %d has unknown kind %d", i, o.kind);

@@ -111,15 +111,24 @@ class MinkUNetEngine:
     def refresh(self):
         """(Re)pack the model's parameters: call again after the weights changed."""
         m = self.model
-        self.w = {}
+        self.w, self.im2col = {}, {}
 
         def put(name, conv, bn):
             w, b = _fold(conv, bn)
             cin = w.shape[1]
             if cin % 32 == 0:       # tensor-core op: [k3, cout, cin]
                 self.w[name] = (w.transpose(1, 2).contiguous(), b.contiguous() if b is not None else None, 0)
-            else:                   # small-cin op keeps [k3, cin, cout]
-                self.w[name] = (w.contiguous(), b.contiguous() if b is not None else None, 1)
+            else:
+                # small input width (the 3-channel 5^3 stem): im2col + one [N, K^3*cin -> pad 32] x [., cout] tensor-core product
+                k3, cout = w.shape[0], w.shape[2]
+                kp = (k3 * cin + 31) // 32 * 32
+                kp = (kp + cin - 1) // cin * cin if kp % cin else kp
+                while kp % 32 or kp % cin:
+                    kp += 1
+                wp = torch.zeros((1, kp, cout), dtype=w.dtype, device=w.device)
+                wp[0, :k3 * cin] = w.reshape(k3 * cin, cout)
+                self.w[name] = (wp.transpose(1, 2).contiguous(), b.contiguous() if b is not None else None, 0)
+                self.im2col[name] = (k3, cin, kp)
 
         put("conv0p1s1", m.conv0p1s1, m.bn0)
         for conv, bn, block in _ENCODER + _DECODER:
@@ -205,7 +214,17 @@ class MinkUNetEngine:
         arena.items += list(skip.values())
         # stem: conv0 (5^3, stride 1) + bn0 + relu -> skip slot of level 1
         src = _Slice(feats.data_ptr(), feats.shape[0], feats.shape[1], 0, feats.shape[1])
-        self._op(ops, "conv0p1s1", src, skip[1], cm.kernel_map(1, self.model.conv0p1s1.kernel_size), relu=True)
+        stem_table = cm.kernel_map(1, self.model.conv0p1s1.kernel_size)
+        if "conv0p1s1" in self.im2col:
+            k3, cin, kp = self.im2col["conv0p1s1"]
+            col = arena.matrix(n[1], kp)
+            o = _lib.ScOp()
+            o.kind, o.cin, o.cout, o.k3, o.ldi, o.ldo, o.n_out, o.n_in = 2, cin, kp, k3, src.ld, kp, n[1], src.rows
+            o.table = stem_table.data_ptr()
+            ops.append((o, src, col, None))
+            self._op(ops, "conv0p1s1", col, skip[1], self._identity(cm, 1), relu=True)
+        else:
+            self._op(ops, "conv0p1s1", src, skip[1], stem_table, relu=True)
         x, ts = skip[1], 1
         for (conv, bn, block), skip_ts in zip(_ENCODER, (2, 4, 8, None)):
             d = cm.down(ts)

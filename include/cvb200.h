@@ -191,6 +191,7 @@ int cvb200_sc_set_conv_impl(int32_t impl);
  * CUDA-core path for the 3-channel stem, w = [k3,cin,cout], cin <= 8, cout % 32 == 0. */
 #define CVB200_OP_CONV_TC 0
 #define CVB200_OP_CONV_SMALLCIN 1
+#define CVB200_OP_IM2COL 2        /* out[o, k*cin + c] = in[table[o,k], c] (0 if missing / padding), ldo % cin == 0 */
 typedef struct cvb200_sc_op {
     int32_t kind, cin, cout, k3;
     int32_t ldi, ldo, ldr, relu;
