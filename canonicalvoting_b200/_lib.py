@@ -30,7 +30,7 @@ SIGNATURES = {
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
 }
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class BpParams(ctypes.Structure):
@@ -57,6 +57,7 @@ SIGNATURES.update({
     "cvb200_sc_conv_forward": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
     "cvb200_sc_conv_forward_tc": (ctypes.c_int, [_f, _i64, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
     "cvb200_sc_set_conv_impl": (ctypes.c_int, [_i32]),
+    "cvb200_sc_set_conv_options": (ctypes.c_int, [_i32, _i32]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
 })
 

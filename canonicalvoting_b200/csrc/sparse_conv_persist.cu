@@ -1,0 +1,422 @@
+// canonicalvoting_b200/csrc/sparse_conv_persist.cu -- persistent, warp-specialised tcgen05 sparse convolution.
+//
+//     out[o, n0:n0+nc) = [relu]( sum_k in[nbr[o,k], :] @ Wt[k][n0:n0+nc, :]^T + bias + residual )
+//
+// Third generation of the tensor-core forward (sparse_conv_tc.cu: CTA-wide barrier per k-block; sparse_conv_tma.cu:
+// warp-specialised, one tile per CTA).  The ncu captures of round 1 (profiles/r1n_*) showed that a third of a CTA's
+// life was prologue (neighbour tile staging) and epilogue (TMEM read-back), serial with the MMA loop, and that the
+// 1.3-wave grids of the large levels left 30 % of the SM-cycles idle; the small levels paid a memset, float atomics
+// and a finishing launch per convolution.  This kernel removes those:
+//   * ONE CTA per SM walks a list of work units.  A unit = (row tile of 128 outputs, channel split, piece of the
+//     k-block sequence); the host plans whole tiles for the full waves and cuts the tiles of the last, partial wave
+//     (or all tiles of a small level) into `ks` pieces so that every SM gets the same amount of k-blocks.
+//   * roles: warp 0 = weight-tile TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-5 = gather
+//     producers (16-byte cp.async straight from the feature matrix into the 128B-swizzled A tile, zero-length copy =
+//     zero fill for a missing neighbour; neighbour ids are read from the table one offset ahead, no staging pass),
+//     warps 6-9 = epilogue.  full/empty mbarriers per ring stage (up to 8 stages, ~200 KB of shared memory).
+//   * TWO accumulators in tensor memory: the epilogue of unit i (tcgen05.ld -> bias/residual/ReLU -> global) runs
+//     while the MMA warp already accumulates unit i+1.
+//   * pieces of a split tile add their partial sums into a zero-initialised, self-cleaning scratch tile
+//     (red.global.add.v4.f32, coalesced [4-column group][row] layout); the piece that arrives last (per-tile counter)
+//     reads the sum back, re-zeroes the scratch and applies the epilogue -- no memset, no finishing launch.
+//   * programmatic dependent launch: barrier init and the TMEM allocation of convolution i+1 overlap the tail of
+//     convolution i (griddepcontrol.wait before the first global read).
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace cvb200 {
+
+constexpr int kPsM = 128, kPsKB = 32, kPsThreads = 320, kPsMaxStages = 8;
+constexpr int kPsMaxSplitTiles = kNumSMs;                    // tiles that can be split in one launch (one partial wave)
+constexpr size_t kPsScratchFloats = (size_t)kPsMaxSplitTiles * kPsM * 128;
+
+struct PsHeader {
+    unsigned long long full_bar[kPsMaxStages], empty_bar[kPsMaxStages], acc_full[2], acc_empty[2];
+    unsigned int tmem_base;
+    int last_flag;
+};
+
+struct PsPlan {
+    int n_tiles;      // row tiles x channel splits
+    int n_splits;     // channel splits (tile t -> row tile t / n_splits, channel block t % n_splits)
+    int n_whole;      // tiles [0, n_whole) are one unit each
+    int ks;           // tiles [n_whole, n_tiles) are cut into ks pieces of the k-block sequence
+    int n_units;
+    int total_kb;     // k3 * cin / 32
+    int cblocks;      // cin / 32
+    int stages;
+    int nc;           // output channels per tile
+    int acc_stride;   // TMEM column offset of the second accumulator
+    int tmem_cols;
+};
+
+struct PsUnit {
+    int row0, n0, kb0, kb1, pieces, split_tile;
+};
+
+__device__ __forceinline__ PsUnit ps_unit(const PsPlan &P, int u) {
+    int tile, piece, pieces;
+    if (u < P.n_whole) {
+        tile = u; piece = 0; pieces = 1;
+    } else {
+        const int v = u - P.n_whole;
+        tile = P.n_whole + v / P.ks; piece = v % P.ks; pieces = P.ks;
+    }
+    PsUnit U;
+    U.row0 = (tile / P.n_splits) * kPsM;
+    U.n0 = (tile % P.n_splits) * P.nc;
+    U.kb0 = (int)((long long)piece * P.total_kb / pieces);
+    U.kb1 = (int)((long long)(piece + 1) * P.total_kb / pieces);
+    U.pieces = pieces;
+    U.split_tile = tile - P.n_whole;
+    return U;
+}
+
+__device__ __forceinline__ void ps_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// dynamic smem: [header 1 KiB][stages x (A 16 KiB | B nc x 128 B)]
+__global__ void __launch_bounds__(kPsThreads, 1)
+sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *__restrict__ in, int ldi, int cout_total,
+                       const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
+                       const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P,
+                       float *__restrict__ scratch, int *__restrict__ counters) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    PsHeader &H = *reinterpret_cast<PsHeader *>(smem);
+    unsigned char *stage0 = smem + 1024;
+    const int a_bytes = kPsM * 128, b_bytes = P.nc * 128, stage_bytes = a_bytes + b_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < P.stages; s++) {
+            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), 1 + 128);
+            tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), 1);
+            tm_mbar_init(tm_smem_u32(&H.acc_empty[b]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tm_smem_u32(&H.tmem_base)), "r"(P.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = H.tmem_base;
+    // everything above overlapped the previous kernel of the stream; its results are visible after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        // ===== weight producer: one TMA load of the [nc x 32] block of Wt[k] per k-block
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+                const PsUnit U = ps_unit(P, u);
+                int k = U.kb0 / P.cblocks, cb = U.kb0 - k * P.cblocks;
+                for (int it = U.kb0; it < U.kb1; it++) {
+                    tm_mbar_wait(tm_smem_u32(&H.empty_bar[s]), ph ^ 1u);
+                    const uint32_t b_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes) + a_bytes;
+                    const uint32_t full = tm_smem_u32(&H.full_bar[s]);
+                    tm_expect_tx(full, (uint32_t)b_bytes);
+                    tma_load_2d(b_s, &map_b, full, cb * kPsKB, k * cout_total + U.n0);
+                    if (++s == P.stages) { s = 0; ph ^= 1u; }
+                    if (++cb == P.cblocks) { cb = 0; k++; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread; accumulator (li & 1) in tensor memory
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.nc >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
+            int s = 0, li = 0;
+            uint32_t ph = 0;
+            for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
+                const PsUnit U = ps_unit(P, u);
+                const int buf = li & 1;
+                tm_mbar_wait(tm_smem_u32(&H.acc_empty[buf]), (uint32_t)(((li >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * P.acc_stride);
+                for (int it = U.kb0; it < U.kb1; it++) {
+                    tm_mbar_wait(tm_smem_u32(&H.full_bar[s]), ph);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
+                    const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
+#pragma unroll
+                    for (int kk = 0; kk < kPsKB / 8; kk++)
+                        tm_umma_tf32(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > U.kb0 || kk > 0) ? 1u : 0u);
+                    tm_commit(tm_smem_u32(&H.empty_bar[s]));
+                    if (++s == P.stages) { s = 0; ph ^= 1u; }
+                }
+                tm_commit(tm_smem_u32(&H.acc_full[buf]));
+            }
+        }
+    } else if (warp < 6) {
+        // ===== gather producers: thread (rb, c) copies the 16-byte chunk c of rows rb + 16 j of every k-block
+        const int pt = tid - 64, c = pt & 7, rb = pt >> 3;
+        uint32_t t_off[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = rb + 16 * j;
+            t_off[j] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            const PsUnit U = ps_unit(P, u);
+            int k = U.kb0 / P.cblocks, cb = U.kb0 - k * P.cblocks;
+            const int *nrow[8];
+            int idx[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r = U.row0 + rb + 16 * j;
+                nrow[j] = r < n_out ? nbr + (size_t)r * k3 : nullptr;
+                idx[j] = nrow[j] ? __ldg(nrow[j] + k) : -1;
+            }
+            const float *a_src[8];
+            uint32_t a_ok[8];
+            bool fresh = true;
+            for (int it = U.kb0; it < U.kb1; it++) {
+                if (fresh) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        a_src[j] = in + (size_t)(idx[j] >= 0 ? idx[j] : 0) * ldi + c * 4;
+                        a_ok[j] = idx[j] >= 0 ? 16u : 0u;
+                    }
+                    if (k + 1 < k3) {   // neighbour ids of the next offset: in flight while this offset's k-blocks are copied
+#pragma unroll
+                        for (int j = 0; j < 8; j++) idx[j] = nrow[j] ? __ldg(nrow[j] + k + 1) : -1;
+                    }
+                    fresh = false;
+                }
+                tm_mbar_wait(tm_smem_u32(&H.empty_bar[s]), ph ^ 1u);
+                const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_s + t_off[j]), "l"(a_src[j] + cb * kPsKB), "r"(a_ok[j]) : "memory");
+                // the hardware arrives on the stage's full barrier when this thread's copies have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
+                if (++s == P.stages) { s = 0; ph ^= 1u; }
+                if (++cb == P.cblocks) { cb = 0; k++; fresh = true; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 6..9: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
+        const int q = warp & 3, et = tid - 192;
+        int li = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
+            const PsUnit U = ps_unit(P, u);
+            const int buf = li & 1;
+            tm_mbar_wait(tm_smem_u32(&H.acc_full[buf]), (uint32_t)((li >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r = U.row0 + q * 32 + lane;
+            const uint32_t taddr0 = tmem + (uint32_t)(buf * P.acc_stride) + ((uint32_t)(q * 32) << 16);
+            const bool split = U.pieces > 1;
+            float *part = scratch + (size_t)U.split_tile * (kPsM * 128);   // [4-column group][128 rows] float4
+            bool finish = !split;
+            if (split) {
+                for (int cb = 0; cb < P.nc / 16; cb++) {
+                    uint32_t v[16];
+                    ps_tmem_ld16(taddr0 + (uint32_t)(cb * 16), v);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float *dst = part + ((size_t)(cb * 4 + j) * kPsM + q * 32 + lane) * 4;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v[4 * j])),
+                                     "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3])) : "memory");
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.acc_empty[buf])) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    __threadfence();
+                    const int old = atomicAdd(counters + U.split_tile, 1);
+                    const int last = old == U.pieces - 1;
+                    if (last) counters[U.split_tile] = 0;
+                    __threadfence();
+                    H.last_flag = last;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                finish = H.last_flag != 0;
+            }
+            if (finish) {
+                const bool row_ok = r < n_out;
+                for (int cb = 0; cb < P.nc / 16; cb++) {
+                    float4 o[4];
+                    if (!split) {
+                        uint32_t v[16];
+                        ps_tmem_ld16(taddr0 + (uint32_t)(cb * 16), v);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                               __uint_as_float(v[4 * j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            float4 *src = reinterpret_cast<float4 *>(part + ((size_t)(cb * 4 + j) * kPsM + q * 32 + lane) * 4);
+                            o[j] = __ldcg(src);
+                            __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));   // the scratch tile is zero again for its next user
+                        }
+                    }
+                    if (row_ok) {
+                        float *dst = out + (size_t)r * ldo + U.n0 + cb * 16;
+                        const float *res = residual ? residual + (size_t)r * ldr + U.n0 + cb * 16 : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (bias) {
+                                const float *bp = bias + U.n0 + cb * 16 + 4 * j;
+                                o[j].x += __ldg(bp); o[j].y += __ldg(bp + 1); o[j].z += __ldg(bp + 2); o[j].w += __ldg(bp + 3);
+                            }
+                            if (res) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4 *>(res) + j);
+                                o[j].x += rv.x; o[j].y += rv.y; o[j].z += rv.z; o[j].w += rv.w;
+                            }
+                            if (relu) {
+                                o[j].x = fmaxf(o[j].x, 0.f); o[j].y = fmaxf(o[j].y, 0.f); o[j].z = fmaxf(o[j].z, 0.f); o[j].w = fmaxf(o[j].w, 0.f);
+                            }
+                            reinterpret_cast<float4 *>(dst)[j] = o[j];
+                        }
+                    }
+                }
+                if (!split) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.acc_empty[buf])) : "memory");
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------- host side
+int g_ps_allow_split = 1;   // 0: never cut tiles into pieces (bit-reproducible summation order; used by the tests)
+int g_ps_use_pdl = 1;
+
+// per-(device, stream) scratch: zero-initialised partial-sum tiles + arrival counters, both self-cleaning
+struct PsWorkspace {
+    float *scratch = nullptr;
+    int *counters = nullptr;
+};
+
+static int ps_workspace(cudaStream_t stream, PsWorkspace *ws) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, PsWorkspace> table;
+    int dev = 0;
+    CVB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = table.find({dev, stream});
+    if (it == table.end()) {
+        PsWorkspace w;
+        const size_t bytes = kPsScratchFloats * sizeof(float) + 4096;
+        void *p = nullptr;
+        CVB_CUDA(cudaMalloc(&p, bytes));
+        CVB_CUDA(cudaMemset(p, 0, bytes));
+        w.counters = reinterpret_cast<int *>(p);
+        w.scratch = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(p) + 4096);
+        it = table.emplace(std::make_pair(dev, stream), w).first;
+    }
+    *ws = it->second;
+    return 0;
+}
+
+static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P) {
+    const int m_tiles = (int)ceil_div(n_out, kPsM);
+    int n_splits = 1;
+    while (cout / n_splits > 128 || cout % n_splits != 0 || (cout / n_splits) % 16 != 0) n_splits++;
+    P->n_splits = n_splits;
+    P->nc = cout / n_splits;
+    P->n_tiles = m_tiles * n_splits;
+    P->cblocks = cin / kPsKB;
+    P->total_kb = k3 * P->cblocks;
+    const int S = kNumSMs;
+    P->n_whole = (P->n_tiles / S) * S;
+    const int R = P->n_tiles - P->n_whole;
+    int best_ks = 1;
+    if (R > 0 && g_ps_allow_split) {
+        // rounds of the partial wave x (k-blocks per piece + fixed cost of a unit) + cost of the split epilogue, in k-block units
+        double best = 1e30;
+        for (int ks = 1; ks <= 32 && ks <= P->total_kb; ks++) {
+            const int rounds = (int)ceil_div((int64_t)R * ks, S);
+            const int per = (int)ceil_div(P->total_kb, ks);
+            const double cost = rounds * (per + 6.0) + (ks > 1 ? 8.0 : 0.0);
+            if (cost < best - 1e-9) { best = cost; best_ks = ks; }
+        }
+    }
+    P->ks = best_ks;
+    if (best_ks == 1) P->n_whole = P->n_tiles;
+    P->n_units = P->n_whole + (P->n_tiles - P->n_whole) * P->ks;
+    const int stage_bytes = kPsM * 128 + P->nc * 128;
+    int stages = (200 * 1024 - 1024) / stage_bytes;
+    P->stages = stages > kPsMaxStages ? kPsMaxStages : stages;
+    int cols = 32;
+    while (cols < 2 * P->nc) cols <<= 1;
+    P->tmem_cols = cols;
+    P->acc_stride = cols / 2;
+}
+
+int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
+                        int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
+                        cudaStream_t stream) {
+    CVB_REQUIRE(cin > 0 && cin % kPsKB == 0 && cout >= 16 && cout <= 1024 && cout % 16 == 0 && k3 > 0, CVB200_EINVAL,
+                "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout (got %d, %d, %d)", cin, cout, k3);
+    CVB_REQUIRE(n_out >= 0 && n_out < (1LL << 31) && n_in > 0 && n_in < (1LL << 31), CVB200_EINVAL, "sc_conv_forward_tc: bad n_out / n_in");
+    if (n_out == 0) return 0;
+    CVB_REQUIRE(d_in && d_wt && d_nbr && d_out, CVB200_EINVAL, "sc_conv_forward_tc: NULL argument");
+    CVB_REQUIRE(((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_wt) | reinterpret_cast<uintptr_t>(d_out) |
+                  reinterpret_cast<uintptr_t>(d_res)) & 15) == 0 && ldi % 4 == 0 && ldo % 4 == 0 && ldr % 4 == 0,
+                CVB200_EINVAL, "sc_conv_forward_tc: 16-byte aligned pointers and row strides required");
+    PsPlan P;
+    ps_plan(n_out, cin, cout, k3, &P);
+    PsWorkspace ws;
+    if (int rc = ps_workspace(stream, &ws)) return rc;
+    alignas(64) CUtensorMap map_b;
+    if (int rc = make_map_2d(&map_b, d_wt, (uint64_t)cin, (uint64_t)k3 * cout, (uint64_t)cin * 4, kPsKB, (uint32_t)P.nc)) return rc;
+    const size_t smem = 1024 + (size_t)P.stages * (kPsM * 128 + P.nc * 128);
+    static bool set = false;
+    if (!set) {
+        CVB_CUDA(cudaFuncSetAttribute(sc_conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(P.n_units < kNumSMs ? P.n_units : kNumSMs));
+    cfg.blockDim = dim3(kPsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_ps_use_pdl ? 1 : 0;
+    CVB_CUDA(cudaLaunchKernelEx(&cfg, sc_conv_persist_kernel, map_b, d_in, ldi, cout, (const int *)d_nbr, (int)n_out, k3, d_bias, d_res,
+                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters));
+    return 0;
+}
+
+}  // namespace cvb200
+
+extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) {
+    cvb200::g_ps_allow_split = allow_split != 0;
+    cvb200::g_ps_use_pdl = use_pdl != 0;
+    return 0;
+}

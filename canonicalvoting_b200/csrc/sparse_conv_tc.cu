@@ -277,12 +277,18 @@ int launch_finish(float *d_out, int ldo, int64_t n_out, int cout, const float *d
 int launch_conv_tma(int gather_a, const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                     int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
                     cudaStream_t stream);
-// 2: warp-specialised kernel, A by cp.async producers + B by TMA (sparse_conv_tma.cu); 1: same kernel, A by TMA gather4;
-// 0: cp.async kernel with a CTA-wide barrier per k-block (this file)
-int g_conv_impl = 2;
+int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
+                        int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
+                        cudaStream_t stream);
+// 3: persistent warp-specialised kernel, two TMEM accumulators, split tiles reduced in-kernel (sparse_conv_persist.cu);
+// 2: warp-specialised kernel, one tile per CTA, A by cp.async producers + B by TMA (sparse_conv_tma.cu); 1: same kernel, A by
+// TMA gather4; 0: cp.async kernel with a CTA-wide barrier per k-block (this file)
+int g_conv_impl = 3;
 
 int launch_conv_tc(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out,
                    int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream) {
+    if (g_conv_impl == 3)
+        return launch_conv_persist(d_in, n_in, ldi, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, d_res, ldr, relu, d_out, ldo, stream);
     if (g_conv_impl != 0)
         return launch_conv_tma(g_conv_impl == 1, d_in, n_in, ldi, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, d_res, ldr, relu, d_out, ldo, stream);
     CVB_REQUIRE(cin > 0 && cin % kTcKB == 0 && cout >= 16 && cout <= 256 && cout % 16 == 0 && k3 > 0 && k3 <= kTcMaxK3,
@@ -346,7 +352,7 @@ extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_
 }
 
 extern "C" int cvb200_sc_set_conv_impl(int32_t impl) {
-    CVB_REQUIRE(impl >= 0 && impl <= 2, CVB200_EINVAL, "sc_set_conv_impl: 0 (cp.async), 1 (TMA gather4) or 2 (cp.async A + TMA B)");
+    CVB_REQUIRE(impl >= 0 && impl <= 3, CVB200_EINVAL, "sc_set_conv_impl: 0 (cp.async), 1 (TMA gather4), 2 (cp.async A + TMA B) or 3 (persistent)");
     g_conv_impl = impl;
     return 0;
 }

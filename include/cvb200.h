@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 8
+#define CVB200_ABI_VERSION 9
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -178,10 +178,16 @@ int cvb200_sc_conv_forward(const float *d_in, int32_t cin, const float *d_w, int
 int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
                               int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
 
-/* Operand movement of the tensor-core convolution (all build the same tiles; selectable for A/B measurements):
- * 2 = warp-specialised kernel, neighbour rows by cp.async producer warps + weight block by TMA (default);
+/* Implementation of the tensor-core convolution (all compute the same contraction; selectable for A/B measurements):
+ * 3 = persistent warp-specialised kernel: one CTA per SM walks work units, two accumulators in tensor memory, tiles of
+ *     the partial wave / of small levels are cut into pieces whose partial sums are combined in-kernel (default);
+ * 2 = warp-specialised kernel, one tile per CTA, neighbour rows by cp.async producer warps + weight block by TMA;
  * 1 = same kernel, neighbour rows by TMA tile::gather4;  0 = cp.async kernel with one CTA barrier per k-block. */
 int cvb200_sc_set_conv_impl(int32_t impl);
+
+/* Options of implementation 3.  allow_split = 0: never cut a tile into pieces (no float atomics: bit-reproducible
+ * results; slower on small levels).  use_pdl = 0: no programmatic dependent launch.  Defaults: 1, 1. */
+int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl);
 
 /* One fused convolution of an inference program (cvb200_sc_run_program):
  *   out[:, 0:cout) (row stride ldo) = [relu]( sum_k in[table[o,k], 0:cin) (row stride ldi) @ W[k] + bias + residual )

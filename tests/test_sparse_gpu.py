@@ -221,25 +221,52 @@ def test_engine_matches_module_path_and_oracle():
     assert out2.shape == (len(coords2), 64) and torch.isfinite(out2).all()
 
 
-def test_tma_gather4_conv_equals_cp_async_conv():
-    """The TMA-fed warp-specialised kernel (tile::gather4 for the neighbour rows, -1 = out-of-bounds = zero fill)
-    builds the same shared-memory tiles as the cp.async kernel: results agree to float-atomic ordering."""
+def test_tensor_core_conv_implementations_agree():
+    """All tcgen05 implementations build the same tiles and compute the same contraction: the persistent kernel
+    (3, default: whole tiles + split tiles reduced in-kernel, PDL), the one-tile-per-CTA warp-specialised kernel with
+    cp.async (2) or TMA tile::gather4 (1) producers, and the CTA-barrier kernel (0) agree to float-atomic ordering."""
     from canonicalvoting_b200 import _lib
     from canonicalvoting_b200.sparse.functional import conv_table_forward
     L = _lib.load()
     g = torch.Generator().manual_seed(3)
     try:
         for (n_in, n_out, cin, cout, k3) in [(500, 130, 64, 32, 27), (3000, 3000, 96, 96, 27), (900, 200, 256, 256, 27),
-                                             (4000, 1000, 128, 96, 8), (700, 700, 96, 64, 1)]:
+                                             (4000, 1000, 128, 96, 8), (700, 700, 96, 64, 1), (2000, 300, 384, 256, 1),
+                                             (30000, 148 * 128 + 5000, 32, 32, 27), (9000, 50000, 64, 96, 8)]:
             table = torch.randint(-1, n_in, (n_out, k3), generator=g, dtype=torch.int64).int()
             table[torch.rand(n_out, k3, generator=g) < 0.5] = -1
             x = torch.randn(n_in, cin, generator=g).cuda()
             w = torch.randn(k3, cin, cout, generator=g).cuda() * 0.1
+            b = torch.randn(1, cout, generator=g).cuda()
             L.cvb200_sc_set_conv_impl(0)
-            ref = conv_table_forward(x, w, table.cuda(), None, mode="tf32")
-            for impl in (1, 2):      # 1: A by TMA gather4; 2 (default): A by cp.async producer warps, B by TMA
+            ref = conv_table_forward(x, w, table.cuda(), b, mode="tf32")
+            for impl, split, pdl in ((1, 1, 1), (2, 1, 1), (3, 0, 0), (3, 1, 0), (3, 1, 1)):
                 L.cvb200_sc_set_conv_impl(impl)
-                got = conv_table_forward(x, w, table.cuda(), None, mode="tf32")
-                assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), (impl, n_in, n_out, cin, cout, k3)
+                L.cvb200_sc_set_conv_options(split, pdl)
+                for rep in range(3 if impl == 3 else 1):     # repeated launches: the split scratch must clean itself
+                    got = conv_table_forward(x, w, table.cuda(), b, mode="tf32")
+                    err, scale = float((got - ref).abs().max()), float(ref.abs().max())
+                    # a different partition of the k-blocks re-associates the fp32 accumulation: a few ulps of the largest sums
+                    tol = 5e-5 if (impl == 3 and split) else 1e-5
+                    assert err <= tol * scale, "impl %d split %d pdl %d rep %d case %s: err %.3e scale %.3e" % (
+                        impl, split, pdl, rep, (n_in, n_out, cin, cout, k3), err, scale)
     finally:
-        L.cvb200_sc_set_conv_impl(2)
+        L.cvb200_sc_set_conv_impl(3)
+        L.cvb200_sc_set_conv_options(1, 1)
+
+
+def test_persistent_conv_without_split_is_bit_reproducible():
+    from canonicalvoting_b200 import _lib
+    from canonicalvoting_b200.sparse.functional import conv_table_forward
+    L = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    table = torch.randint(-1, 900, (700, 27), generator=g, dtype=torch.int64).int().cuda()
+    x = torch.randn(900, 128, generator=g).cuda()
+    w = torch.randn(27, 128, 128, generator=g).cuda() * 0.1
+    try:
+        L.cvb200_sc_set_conv_options(0, 1)
+        a = conv_table_forward(x, w, table, None, mode="tf32")
+        b = conv_table_forward(x, w, table, None, mode="tf32")
+        assert torch.equal(a, b)
+    finally:
+        L.cvb200_sc_set_conv_options(1, 1)
