@@ -247,7 +247,7 @@ def test_tensor_core_conv_implementations_agree():
                     got = conv_table_forward(x, w, table.cuda(), b, mode="tf32")
                     err, scale = float((got - ref).abs().max()), float(ref.abs().max())
                     # a different partition of the k-blocks re-associates the fp32 accumulation: a few ulps of the largest sums
-                    tol = 5e-5 if (impl == 3 and split) else 1e-5
+                    tol = 5e-5
                     assert err <= tol * scale, "impl %d split %d pdl %d rep %d case %s: err %.3e scale %.3e" % (
                         impl, split, pdl, rep, (n_in, n_out, cin, cout, k3), err, scale)
     finally:
