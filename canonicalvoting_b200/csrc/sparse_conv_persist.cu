@@ -33,6 +33,7 @@
 namespace cvb200 {
 
 constexpr int kPsM = 128, kPsKB = 32, kPsThreads = 320, kPsMaxStages = 8;
+constexpr int kPsSmemBytes = 224 * 1024;                   // of the 227 KiB a CTA may use
 constexpr int kPsMaxSplitTiles = kNumSMs;                    // tiles that can be split in one launch (one partial wave)
 constexpr size_t kPsScratchFloats = (size_t)kPsMaxSplitTiles * kPsM * 128;
 
@@ -54,6 +55,7 @@ struct PsPlan {
     int nc;           // output channels per tile
     int acc_stride;   // TMEM column offset of the second accumulator
     int tmem_cols;
+    int dbg;          // measurement aid (cvb200_sc_set_conv_debug): 1 no gather copies, 2 no zero-fill copies, 4 no MMA, 8 no weight TMA
 };
 
 struct PsUnit {
@@ -87,21 +89,36 @@ __device__ __forceinline__ void ps_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// dynamic smem: [header 1 KiB][stages x (A 16 KiB | B nc x 128 B)]
+// wait until at most n of this thread's cp.async groups are pending (the PTX operand is an immediate)
+__device__ __forceinline__ void ps_cp_async_wait(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    }
+}
+
+// dynamic smem: [header 1 KiB][epilogue staging: 4 warps x 32 rows x 128 B][stages x (A 16 KiB | B nc x 128 B)]
 __global__ void __launch_bounds__(kPsThreads, 1)
 sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *__restrict__ in, int ldi, int cout_total,
                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
                        const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P,
-                       float *__restrict__ scratch, int *__restrict__ counters) {
+                       float *__restrict__ scratch, int *__restrict__ counters, long long *__restrict__ trace) {
     extern __shared__ __align__(1024) unsigned char smem[];
     PsHeader &H = *reinterpret_cast<PsHeader *>(smem);
-    unsigned char *stage0 = smem + 1024;
+    unsigned char *stage0 = smem + 1024 + 16384;       // [header 1 KiB][epilogue staging 4 x 4 KiB][ring]
     const int a_bytes = kPsM * 128, b_bytes = P.nc * 128, stage_bytes = a_bytes + b_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tr = trace != nullptr && blockIdx.x == 0;   // measurement aid: clock64 stamps of the first 256 k-blocks of CTA 0
+    int tn = 0;
 
     if (tid == 0) {
         for (int s = 0; s < P.stages; s++) {
-            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), 1 + 128);
+            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), 1 + 32);
             tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
@@ -123,99 +140,132 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        // ===== weight producer: one TMA load of the [nc x 32] block of Wt[k] per k-block
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
-                const PsUnit U = ps_unit(P, u);
-                int k = U.kb0 / P.cblocks, cb = U.kb0 - k * P.cblocks;
-                for (int it = U.kb0; it < U.kb1; it++) {
-                    tm_mbar_wait(tm_smem_u32(&H.empty_bar[s]), ph ^ 1u);
-                    const uint32_t b_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes) + a_bytes;
-                    const uint32_t full = tm_smem_u32(&H.full_bar[s]);
-                    tm_expect_tx(full, (uint32_t)b_bytes);
-                    tma_load_2d(b_s, &map_b, full, cb * kPsKB, k * cout_total + U.n0);
-                    if (++s == P.stages) { s = 0; ph ^= 1u; }
-                    if (++cb == P.cblocks) { cb = 0; k++; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: one thread; accumulator (li & 1) in tensor memory
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.nc >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
-            int s = 0, li = 0;
-            uint32_t ph = 0;
-            for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
-                const PsUnit U = ps_unit(P, u);
-                const int buf = li & 1;
-                tm_mbar_wait(tm_smem_u32(&H.acc_empty[buf]), (uint32_t)(((li >> 1) & 1) ^ 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem + (uint32_t)(buf * P.acc_stride);
-                for (int it = U.kb0; it < U.kb1; it++) {
-                    tm_mbar_wait(tm_smem_u32(&H.full_bar[s]), ph);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
-                    const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
-#pragma unroll
-                    for (int kk = 0; kk < kPsKB / 8; kk++)
-                        tm_umma_tf32(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > U.kb0 || kk > 0) ? 1u : 0u);
-                    tm_commit(tm_smem_u32(&H.empty_bar[s]));
-                    if (++s == P.stages) { s = 0; ph ^= 1u; }
-                }
-                tm_commit(tm_smem_u32(&H.acc_full[buf]));
-            }
-        }
-    } else if (warp < 6) {
-        // ===== gather producers: thread (rb, c) copies the 16-byte chunk c of rows rb + 16 j of every k-block
-        const int pt = tid - 64, c = pt & 7, rb = pt >> 3;
-        uint32_t t_off[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int r = rb + 16 * j;
-            t_off[j] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-        }
+        // ===== weight producer: one TMA load of the [nc x 32] block of Wt[k] per k-block.  The whole warp walks the loop
+        // (warp-uniform control flow), one elected lane issues.
         int s = 0;
         uint32_t ph = 0;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             const PsUnit U = ps_unit(P, u);
             int k = U.kb0 / P.cblocks, cb = U.kb0 - k * P.cblocks;
-            const int *nrow[8];
-            int idx[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int r = U.row0 + rb + 16 * j;
-                nrow[j] = r < n_out ? nbr + (size_t)r * k3 : nullptr;
-                idx[j] = nrow[j] ? __ldg(nrow[j] + k) : -1;
-            }
-            const float *a_src[8];
-            uint32_t a_ok[8];
-            bool fresh = true;
             for (int it = U.kb0; it < U.kb1; it++) {
-                if (fresh) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        a_src[j] = in + (size_t)(idx[j] >= 0 ? idx[j] : 0) * ldi + c * 4;
-                        a_ok[j] = idx[j] >= 0 ? 16u : 0u;
-                    }
-                    if (k + 1 < k3) {   // neighbour ids of the next offset: in flight while this offset's k-blocks are copied
-#pragma unroll
-                        for (int j = 0; j < 8; j++) idx[j] = nrow[j] ? __ldg(nrow[j] + k + 1) : -1;
-                    }
-                    fresh = false;
-                }
+                const long long t0 = tr ? clock64() : 0;
                 tm_mbar_wait(tm_smem_u32(&H.empty_bar[s]), ph ^ 1u);
-                const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes);
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_s + t_off[j]), "l"(a_src[j] + cb * kPsKB), "r"(a_ok[j]) : "memory");
-                // the hardware arrives on the stage's full barrier when this thread's copies have landed
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
+                if (tr && lane == 0 && tn < 256) { trace[2 * 768 + 3 * tn] = t0; trace[2 * 768 + 3 * tn + 1] = clock64(); }
+                const uint32_t b_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes) + a_bytes;
+                const uint32_t full = tm_smem_u32(&H.full_bar[s]);
+                if (tm_elect_one()) {
+                    if (P.dbg & 8) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+                    } else {
+                        tm_expect_tx(full, (uint32_t)b_bytes);
+                        tma_load_2d(b_s, &map_b, full, cb * kPsKB, k * cout_total + U.n0);
+                    }
+                }
+                __syncwarp();
+                if (tr && lane == 0 && tn < 256) { trace[2 * 768 + 3 * tn + 2] = clock64(); }
+                tn++;
                 if (++s == P.stages) { s = 0; ph ^= 1u; }
-                if (++cb == P.cblocks) { cb = 0; k++; fresh = true; }
+                if (++cb == P.cblocks) { cb = 0; k++; }
             }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues; accumulator (li & 1) in tensor memory
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.nc >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
+        int s = 0, li = 0;
+        uint32_t ph = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
+            const PsUnit U = ps_unit(P, u);
+            const int buf = li & 1;
+            tm_mbar_wait(tm_smem_u32(&H.acc_empty[buf]), (uint32_t)(((li >> 1) & 1) ^ 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem + (uint32_t)(buf * P.acc_stride);
+            for (int it = U.kb0; it < U.kb1; it++) {
+                const long long t0 = tr ? clock64() : 0;
+                tm_mbar_wait(tm_smem_u32(&H.full_bar[s]), ph);
+                if (tr && lane == 0 && tn < 256) { trace[3 * tn] = t0; trace[3 * tn + 1] = clock64(); }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
+                const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
+                if (tm_elect_one()) {
+                    if (!(P.dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
+                    if (!(P.dbg & 4)) {
+#pragma unroll
+                        for (int kk = 0; kk < kPsKB / 8; kk++)
+                            tm_umma_tf32(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > U.kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    tm_commit(tm_smem_u32(&H.empty_bar[s]));
+                }
+                __syncwarp();
+                if (tr && lane == 0 && tn < 256) { trace[3 * tn + 2] = clock64(); }
+                tn++;
+                if (++s == P.stages) { s = 0; ph ^= 1u; }
+            }
+            if (tm_elect_one()) tm_commit(tm_smem_u32(&H.acc_full[buf]));
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===== gather producers.  A single warp's instruction stream (barrier poll, address arithmetic, copies, arrival)
+        // costs ~1000 cycles per k-block whatever the copy count (tools/conv_trace.py), so the four warps do NOT share
+        // a k-block: warp w owns the k-blocks n % 4 == w of the CTA's running k-block sequence and fills their stages
+        // alone -- four k-blocks are being filled at any time.  (n, n + 4 are less than a ring apart, so a warp is never
+        // more than one phase ahead of an empty barrier, which is all a parity wait can tell apart.)  Lane (rb, c) copies
+        // the 16-byte chunk c of rows rb + 4 j, j < 32; completion arrives on the stage's full barrier by itself
+        // (cp.async.mbarrier.arrive.noinc, 32 arrivals per stage), nobody waits for data.
+        const int w = warp - 2, c = lane & 7, rb = lane >> 3;
+        const uint32_t off_even = (uint32_t)(rb * 128 + ((c ^ rb) << 4)), off_odd = (uint32_t)((rb + 4) * 128 + ((c ^ (rb + 4)) << 4));
+        const size_t ld4 = (size_t)ldi;
+        int n_base = 0;
+        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+            const PsUnit U = ps_unit(P, u);
+            // neighbour ids: lane l holds the ids of rows l, l + 32, l + 64, l + 96 for one kernel offset (4 coalesced-ish
+            // loads, issued one k-block ahead); the id of row rb + 4 j reaches lane (rb, c) by a shuffle
+            const int *nlane = nbr + (size_t)(U.row0 + lane) * k3;
+            const int lane_rows = n_out - U.row0 - lane;          // row lane + 32 m exists iff 32 m < lane_rows
+            int cur[4], nxt[4];
+            int it = U.kb0 + ((w - n_base) & 3);
+            int k_cur = -1, k_nxt = -1;
+            if (it < U.kb1) {
+                k_nxt = it / P.cblocks;
+#pragma unroll
+                for (int m = 0; m < 4; m++) nxt[m] = 32 * m < lane_rows ? __ldg(nlane + (size_t)(32 * m) * k3 + k_nxt) : -1;
+            }
+            for (; it < U.kb1; it += 4) {
+                const int k = it / P.cblocks, cb = it - k * P.cblocks;
+                if (k != k_cur) {       // k == k_nxt by construction
+#pragma unroll
+                    for (int m = 0; m < 4; m++) cur[m] = nxt[m];
+                    k_cur = k;
+                }
+                if (it + 4 < U.kb1) {
+                    const int kn = (it + 4) / P.cblocks;
+                    if (kn != k_cur) {
+#pragma unroll
+                        for (int m = 0; m < 4; m++) nxt[m] = 32 * m < lane_rows ? __ldg(nlane + (size_t)(32 * m) * k3 + kn) : -1;
+                        k_nxt = kn;
+                    }
+                }
+                const int n = n_base + it - U.kb0;
+                const int round = n / P.stages, s = n - round * P.stages;
+                const long long t0 = tr ? clock64() : 0;
+                if (lane == 0) tm_mbar_spin(tm_smem_u32(&H.empty_bar[s]), (uint32_t)((round & 1) ^ 1));
+                __syncwarp();
+                if (tr && tid == 64 && tn < 256) { trace[768 + 3 * tn] = t0; trace[768 + 3 * tn + 1] = clock64(); }
+                const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes);
+                const float *src0 = in + c * 4 + cb * kPsKB;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int id = __shfl_sync(0xffffffffu, cur[j >> 3], rb + 4 * (j & 7));   // row rb + 4 j = 32 (j >> 3) + rb + 4 (j & 7)
+                    const float *src = src0 + (size_t)(id >= 0 ? id : 0) * ld4;
+                    const uint32_t dst = a_s + ((j & 1) ? off_odd : off_even) + (uint32_t)((j >> 1) * 1024);
+                    if (!(P.dbg & 1))
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(id >= 0 ? 16u : 0u) : "memory");
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
+                if (tr && tid == 64 && tn < 256) { trace[768 + 3 * tn + 2] = clock64(); }
+                tn++;
+            }
+            (void)k_nxt;
+            n_base += U.kb1 - U.kb0;
         }
     } else {
         // ===== epilogue warps 6..9: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
@@ -224,7 +274,10 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
             const int buf = li & 1;
-            tm_mbar_wait(tm_smem_u32(&H.acc_full[buf]), (uint32_t)((li >> 1) & 1));
+            // one polling lane per warp: 128 threads parked in try_wait on the header slowed every other mbarrier operation
+            // of the CTA down (tools/conv_trace.py)
+            if (lane == 0 || (P.dbg & 128)) tm_mbar_wait(tm_smem_u32(&H.acc_full[buf]), (uint32_t)((li >> 1) & 1));
+            __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int r = U.row0 + q * 32 + lane;
             const uint32_t taddr0 = tmem + (uint32_t)(buf * P.acc_stride) + ((uint32_t)(q * 32) << 16);
@@ -235,6 +288,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 for (int cb = 0; cb < P.nc / 16; cb++) {
                     uint32_t v[16];
                     ps_tmem_ld16(taddr0 + (uint32_t)(cb * 16), v);
+                    if (r < n_out)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         float *dst = part + ((size_t)(cb * 4 + j) * kPsM + q * 32 + lane) * 4;
@@ -257,7 +311,76 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 finish = H.last_flag != 0;
             }
-            if (finish) {
+            if (finish && (P.nc & 31) == 0) {
+                // Coalesced write-out: 32-column chunks go through a swizzled per-warp staging tile, so that a warp
+                // instruction stores (and reads the residual of) 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
+                // (The uncoalesced version kept so many sectors in flight that the MMA warp's proxy fence -- a MEMBAR --
+                // stalled ~7500 cycles per chunk and with it the whole ring: 159 -> 90 us on the 96-channel 3^3 layers.)
+                const bool row_ok = r < n_out;
+                const uint32_t st = tm_smem_u32(smem + 1024 + q * 4096);
+                const int g = lane & 7, sub = lane >> 3;
+                for (int ch = 0; ch < P.nc / 32; ch++) {
+                    uint32_t v[32];
+                    if (!split) {
+                        if (P.dbg & 0x20000) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) v[j] = 0u;
+                        } else {
+                            uint32_t lo[16], hi[16];
+                            ps_tmem_ld16(taddr0 + (uint32_t)(ch * 32), lo);
+                            ps_tmem_ld16(taddr0 + (uint32_t)(ch * 32 + 16), hi);
+#pragma unroll
+                            for (int j = 0; j < 16; j++) { v[j] = lo[j]; v[16 + j] = hi[j]; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 *src = reinterpret_cast<float4 *>(part + ((size_t)(ch * 8 + j) * kPsM + q * 32 + lane) * 4);
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (row_ok) {
+                                t = __ldcg(src);
+                                __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));   // the scratch tile is zero again for its next user
+                            }
+                            v[4 * j] = __float_as_uint(t.x); v[4 * j + 1] = __float_as_uint(t.y);
+                            v[4 * j + 2] = __float_as_uint(t.z); v[4 * j + 3] = __float_as_uint(t.w);
+                        }
+                    }
+                    const int col = U.n0 + ch * 32 + g * 4;
+                    float4 rv[8];
+                    if (residual && !(P.dbg & 0x10000)) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int rr = U.row0 + q * 32 + 4 * i + sub;
+                            rv[i] = rr < n_out ? __ldg(reinterpret_cast<const float4 *>(residual + (size_t)rr * ldr + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    __syncwarp();                                    // the previous chunk has been read out of the staging tile
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4))),
+                                     "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                    __syncwarp();
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) bv = __ldg(reinterpret_cast<const float4 *>(bias + col));
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int row = 4 * i + sub, rr = U.row0 + q * 32 + row;
+                        float4 o;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                                     : "r"(st + (uint32_t)(row * 128 + ((g ^ (row & 7)) << 4))) : "memory");
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        if (residual && !(P.dbg & 0x10000)) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (rr < n_out && !(P.dbg & 0x10000)) *reinterpret_cast<float4 *>(out + (size_t)rr * ldo + col) = o;
+                    }
+                }
+                if (!split) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.acc_empty[buf])) : "memory");
+                }
+            } else if (finish) {
+                // channel counts that are not a multiple of 32: direct 16-byte stores per row
                 const bool row_ok = r < n_out;
                 for (int cb = 0; cb < P.nc / 16; cb++) {
                     float4 o[4];
@@ -268,12 +391,12 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                         for (int j = 0; j < 4; j++)
                             o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                                __uint_as_float(v[4 * j + 3]));
-                    } else {
+                    } else if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             float4 *src = reinterpret_cast<float4 *>(part + ((size_t)(cb * 4 + j) * kPsM + q * 32 + lane) * 4);
                             o[j] = __ldcg(src);
-                            __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));   // the scratch tile is zero again for its next user
+                            __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));
                         }
                     }
                     if (row_ok) {
@@ -312,6 +435,8 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
 // ---------------------------------------------------------------------------------------------------------- host side
 int g_ps_allow_split = 1;   // 0: never cut tiles into pieces (bit-reproducible summation order; used by the tests)
 int g_ps_use_pdl = 1;
+int g_ps_debug = 0;
+long long *g_ps_trace = nullptr;
 
 // per-(device, stream) scratch: zero-initialised partial-sum tiles + arrival counters, both self-cleaning
 struct PsWorkspace {
@@ -363,16 +488,19 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P) {
             if (cost < best - 1e-9) { best = cost; best_ks = ks; }
         }
     }
+    if (((g_ps_debug >> 8) & 255) > 0 && R > 0) best_ks = ((g_ps_debug >> 8) & 255) < P->total_kb ? ((g_ps_debug >> 8) & 255) : P->total_kb;   // probe override
     P->ks = best_ks;
     if (best_ks == 1) P->n_whole = P->n_tiles;
     P->n_units = P->n_whole + (P->n_tiles - P->n_whole) * P->ks;
     const int stage_bytes = kPsM * 128 + P->nc * 128;
-    int stages = (200 * 1024 - 1024) / stage_bytes;
+    int stages = (kPsSmemBytes - 1024 - 16384) / stage_bytes;
     P->stages = stages > kPsMaxStages ? kPsMaxStages : stages;
     int cols = 32;
     while (cols < 2 * P->nc) cols <<= 1;
     P->tmem_cols = cols;
     P->acc_stride = cols / 2;
+    P->dbg = g_ps_debug & 0xff00ff;
+
 }
 
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
@@ -392,10 +520,10 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     if (int rc = ps_workspace(stream, &ws)) return rc;
     alignas(64) CUtensorMap map_b;
     if (int rc = make_map_2d(&map_b, d_wt, (uint64_t)cin, (uint64_t)k3 * cout, (uint64_t)cin * 4, kPsKB, (uint32_t)P.nc)) return rc;
-    const size_t smem = 1024 + (size_t)P.stages * (kPsM * 128 + P.nc * 128);
+    const size_t smem = 1024 + 16384 + (size_t)P.stages * (kPsM * 128 + P.nc * 128);
     static bool set = false;
     if (!set) {
-        CVB_CUDA(cudaFuncSetAttribute(sc_conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CVB_CUDA(cudaFuncSetAttribute(sc_conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemBytes));
         set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -409,7 +537,7 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     cfg.attrs = attr;
     cfg.numAttrs = g_ps_use_pdl ? 1 : 0;
     CVB_CUDA(cudaLaunchKernelEx(&cfg, sc_conv_persist_kernel, map_b, d_in, ldi, cout, (const int *)d_nbr, (int)n_out, k3, d_bias, d_res,
-                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters));
+                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace));
     return 0;
 }
 
@@ -418,5 +546,19 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
 extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) {
     cvb200::g_ps_allow_split = allow_split != 0;
     cvb200::g_ps_use_pdl = use_pdl != 0;
+    return 0;
+}
+
+/* Measurement aid: switch off parts of the persistent kernel (results become garbage): 1 no gather copies, 2 no zero-fill
+ * copies, 4 no MMA, 8 no weight TMA.  0 = normal operation. */
+extern "C" int cvb200_sc_set_conv_debug(int32_t mask) {
+    cvb200::g_ps_debug = mask;
+    return 0;
+}
+
+/* Measurement aid: device buffer of 3 x 768 int64 receiving clock64 stamps (before wait, after wait, after issue) of the
+ * first 256 k-blocks of CTA 0 for the MMA thread, gather warp 2 and the weight-TMA thread.  NULL switches it off. */
+extern "C" int cvb200_sc_set_conv_trace(void *d_trace) {
+    cvb200::g_ps_trace = (long long *)d_trace;
     return 0;
 }

@@ -189,6 +189,13 @@ int cvb200_sc_set_conv_impl(int32_t impl);
  * results; slower on small levels).  use_pdl = 0: no programmatic dependent launch.  Defaults: 1, 1. */
 int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl);
 
+/* Measurement aid (tools/conv_probe.py): switch off parts of implementation 3 to find which side bounds it -- results are
+ * garbage while mask != 0.  1 = no gather copies, 2 = no zero-fill copies, 4 = no MMA, 8 = no weight TMA. */
+int cvb200_sc_set_conv_debug(int32_t mask);
+/* Measurement aid: device buffer of 3 x 768 int64 that receives clock64 stamps (before wait, after wait, after issue) of the
+ * first 256 k-blocks of CTA 0 for the MMA thread, one gather warp and the weight-TMA thread; NULL switches it off. */
+int cvb200_sc_set_conv_trace(void *d_trace);
+
 /* One fused convolution of an inference program (cvb200_sc_run_program):
  *   out[:, 0:cout) (row stride ldo) = [relu]( sum_k in[table[o,k], 0:cin) (row stride ldi) @ W[k] + bias + residual )
  * `in`, `out` and `residual` may point into column slices of wider buffers (that is how ME.cat,
