@@ -227,6 +227,12 @@ def main():
     from canonicalvoting_b200 import hv_cuda as H
     from canonicalvoting_b200.engine import MinkUNetEngine
 
+    if os.environ.get("CVB200_CONV_OPTS"):      # A/B switch for measurements: "<allow_split>,<use_pdl>[,<impl>]"
+        from canonicalvoting_b200 import _lib
+        o = [int(x) for x in os.environ["CVB200_CONV_OPTS"].split(",")]
+        _lib.load().cvb200_sc_set_conv_options(o[0], o[1])
+        if len(o) > 2:
+            _lib.load().cvb200_sc_set_conv_impl(o[2])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -288,14 +294,23 @@ def main():
         dev_scenes.append((c_d, f_d, cr, dm))
     torch.cuda.synchronize()
 
-    def step_scene(j):
+    def step_scene(j, maps=None):
         c_d, f_d, cr, dm = dev_scenes[j % n_rot]
-        xyz, scale, cls, prob = engine.predict(c_d, f_d)
+        xyz, scale, cls, prob = engine.predict(c_d, f_d, maps)
         points = (c_d[:, 1:].float() * res).contiguous()              # eval_joint.py:193
         return H.forward_host(points, xyz, scale, prob, res, R, cr, dm)
 
-    for j in range(args.warmup + n_rot):
-        step_scene(j)
+    def run_steps(k):
+        # the coordinate maps of scene j+1 are built by the engine's worker thread / side stream while scene j is launched
+        fut = engine.prefetch(dev_scenes[0][0])
+        out = None
+        for j in range(k):
+            nxt = engine.prefetch(dev_scenes[(j + 1) % n_rot][0]) if j + 1 < k else None
+            out = step_scene(j, fut)
+            fut = nxt
+        return out
+
+    run_steps(args.warmup + n_rot)
     barrier()
     import gc
     gc.collect()
@@ -303,8 +318,7 @@ def main():
     t0, t1 = ev(), ev()
     with ClockSampler(local) as clk:
         t0.record(stream)
-        for j in range(args.steps):
-            out = step_scene(j)
+        out = run_steps(args.steps)
         t1.record(stream)
         barrier()
     gc.enable()
@@ -328,22 +342,28 @@ def main():
     vote_ms = [m[2].elapsed_time(m[3]) for m in marks]
 
     # ---- end to end through the reference-facing API with HOST buffers
-    def step_e2e():
-        c, f = engine.upload(coords_h, feats_h)            # pinned host -> device on the engine's map stream
-        xyz, scale, cls, prob = engine.predict(c, f)
+    def step_e2e(fut):
+        # fut: upload (pinned host -> device) + coordinate maps of THIS scene, started while the previous scene ran
+        c, f, _, _ = fut.result()
+        xyz, scale, cls, prob = engine.predict(None, None, fut)
         go, gr, gs = hv_cuda.forward((c[:, 1:].float() * res).contiguous(), xyz, scale, prob, res_t, rots_t)
         peak = torch.stack([go.max(), go.argmax().float()])
         return peak.cpu()          # D2H read of the step's result (peak value + voxel)
 
-    for _ in range(args.warmup):
-        step_e2e()
+    def run_e2e(k):
+        fut = engine.prefetch(coords_h, feats_h)
+        for j in range(k):
+            nxt = engine.prefetch(coords_h, feats_h) if j + 1 < k else None
+            step_e2e(fut)
+            fut = nxt
+
+    run_e2e(args.warmup)
     t_e2e = float("inf")
     for _ in range(2):            # two passes of K steps, the steadier one counts (host jitter shows up here: 2 syncs per step)
         barrier()
         e0, e1 = ev(), ev()
         e0.record(stream)
-        for _ in range(args.steps):
-            step_e2e()
+        run_e2e(args.steps)
         e1.record(stream)
         barrier()
         t_e2e = min(t_e2e, e0.elapsed_time(e1) / 1e3)
