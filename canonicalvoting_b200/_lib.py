@@ -72,6 +72,19 @@ class ScOp(ctypes.Structure):
                 ("out", _vp)]
 
 
+class MapsLayout(ctypes.Structure):
+    """cvb200_sc_maps_layout_t (include/cvb200.h)."""
+    _fields_ = [("total_bytes", _i64), ("capacity", _i64), ("counts", _i64), ("arange", _i64), ("stem_table", _i64),
+                ("coords", _i64 * 5), ("keys", _i64 * 5), ("vals", _i64 * 5), ("nbr3", _i64 * 5),
+                ("children", _i64 * 4), ("up_table", _i64 * 4), ("parent", _i64 * 4), ("koff", _i64 * 4),
+                ("flag", _i64), ("scan", _i64), ("cub_temp", _i64), ("cub_temp_bytes", _i64)]
+
+
+SIGNATURES.update({
+    "cvb200_sc_maps_layout": (ctypes.c_int, [_i64, _i32, _i32, ctypes.POINTER(MapsLayout)]),
+    "cvb200_sc_build_maps": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, ctypes.POINTER(MapsLayout), _vp, _vp]),
+})
+
 SIGNATURES.update({
     "cvb200_sc_run_program": (ctypes.c_int, [ctypes.POINTER(ScOp), _i32, _vp]),
     "cvb200_head_decode": (ctypes.c_int, [_f, _i32, _i64, _i32, _i32, _f, _f, _vp, _f, _vp]),

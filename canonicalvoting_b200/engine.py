@@ -101,6 +101,8 @@ class MinkUNetEngine:
         self._side = torch.cuda.Stream(self.device, priority=-1) if pipeline else None
         self._ring = collections.deque()      # (tensors used by launches in flight, completion event)
         self._pool = None                     # one worker thread for prefetch()
+        self._pinned = None                   # count read-back buffer of the fused map builder (one build at a time)
+        self.fused_maps = True                # cvb200_sc_build_maps (one sync per scene); False: step-by-step coordinate manager
         self.refresh()
 
     def upload(self, coords_host, feats_host):
@@ -210,6 +212,10 @@ class MinkUNetEngine:
 
     def build_maps(self, coords):
         """Coordinate levels + every neighbour table the network needs (device work + one scalar read per level)."""
+        if self.fused_maps:
+            if self._pinned is None:
+                self._pinned = torch.empty(8, dtype=torch.int32).pin_memory()
+            return CoordinateManager.build_unet(coords, int(self.model.conv0p1s1.kernel_size), 4, self._pinned)
         cm = CoordinateManager(coords)
         for ts in (1, 2, 4, 8):
             cm.down(ts)

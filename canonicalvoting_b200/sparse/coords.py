@@ -59,6 +59,57 @@ class CoordinateManager:
         self._nbr = {}      # (tensor_stride, ksize) -> [n, ksize^3] int32
         self._down = {}     # fine tensor_stride -> dict(children, up_table, parent, koff)
 
+    # ------------------------------------------------------------------ everything a U-Net needs, one enqueue + one sync
+    @classmethod
+    def build_unet(cls, coords, stem_ksize, n_down=4, pinned_counts=None):
+        """Levels 1, 2, ..., 2^n_down with their 3^3 maps, the stem map of level 1, children / parent tables of every
+        stride-2 step and the identity tables, built by ONE call of cvb200_sc_build_maps (csrc/sparse_maps.cu) on the
+        current stream and ONE synchronisation of it -- instead of a host read-back per level.  The result behaves like a
+        manager on which kernel_map() / down() were already called (same tables, same numbering)."""
+        cm = cls(coords)
+        L = _lib.load()
+        n = cm.levels[1].n
+        lay = _lib.MapsLayout()
+        _lib.check(L.cvb200_sc_maps_layout(n, stem_ksize, n_down, ctypes.byref(lay)), "cvb200_sc_maps_layout")
+        dev = cm.device
+        with torch.cuda.device(dev):
+            ws = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
+            if pinned_counts is None:
+                pinned_counts = torch.empty(8, dtype=torch.int32).pin_memory()
+            stream = torch.cuda.current_stream()
+            rc = L.cvb200_sc_build_maps(_ptr(cm.levels[1].coords), n, stem_ksize, n_down, _ptr(ws), ctypes.byref(lay),
+                                        ctypes.c_void_p(pinned_counts.data_ptr()), _stream())
+            _lib.check(rc, "cvb200_sc_build_maps")
+            stream.synchronize()                                   # the one host synchronisation of the scene
+        counts = [int(v) for v in pinned_counts[:n_down + 1].tolist()]
+
+        def view(off, rows, cols, dtype=torch.int32):
+            nbytes = rows * max(cols, 1) * (8 if dtype == torch.int64 else 4)        # cols == 0: a vector of `rows` elements
+            t = ws[off:off + nbytes].view(dtype)
+            return t.view(rows, cols) if cols else t
+
+        cm._ws = ws
+        arange = view(lay.arange, n, 1)
+        for l in range(n_down + 1):
+            ts = 1 << l
+            if l:
+                lv = Level.__new__(Level)
+                lv.coords, lv.n, lv.tensor_stride = view(lay.coords[l], counts[l], 4), counts[l], ts
+                cm.levels[ts] = lv
+            lv = cm.levels[ts]
+            lv.capacity = int(lay.capacity)
+            lv.keys = view(lay.keys[l], lv.capacity, 0, torch.int64)
+            lv.vals = view(lay.vals[l], lv.capacity, 0)
+            lv.table_built = True
+            cm._nbr[(ts, 3)] = view(lay.nbr3[l], counts[l], 27)
+            cm._nbr[("ident", ts)] = arange[:counts[l]]
+        if stem_ksize:
+            cm._nbr[(1, stem_ksize)] = view(lay.stem_table, n, stem_ksize ** 3)
+        for l in range(n_down):
+            cm._down[1 << l] = dict(children=view(lay.children[l], counts[l + 1], 8), up_table=view(lay.up_table[l], counts[l], 8),
+                                    parent=view(lay.parent[l], counts[l], 0), koff=view(lay.koff[l], counts[l], 0))
+        return cm
+
     # ------------------------------------------------------------------ stride-1 kernel maps
     def kernel_map(self, tensor_stride, ksize):
         key = (tensor_stride, ksize)

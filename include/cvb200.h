@@ -196,6 +196,25 @@ int cvb200_sc_set_conv_debug(int32_t mask);
  * first 256 k-blocks of CTA 0 for the MMA thread, one gather warp and the weight-TMA thread; NULL switches it off. */
 int cvb200_sc_set_conv_trace(void *d_trace);
 
+/* All coordinate levels and kernel maps of a MinkUNet-shaped network in one enqueue, without the host in the loop
+ * (csrc/sparse_maps.cu).  Level l has tensor stride 2^l; every table is allocated for the upper bound n inside ONE workspace
+ * of layout->total_bytes bytes (offsets below are in bytes); the real sizes are written to counts[0 .. n_down] on the
+ * device and copied to h_counts_pinned at the end of the enqueued work: synchronise the stream ONCE, then use
+ * rows [0, counts[l]) of each table.  Tables: coords[l] int32 [.,4]; keys/vals: the level's hash map (capacity entries);
+ * nbr3[l] int32 [.,27] (3^3 map of the level); stem_table int32 [n, stem_ksize^3] (level 0); arange int32 [n] (identity
+ * table of 1x1x1 convolutions); per stride-2 step l -> l+1: children int32 [counts[l+1], 8], up_table int32
+ * [counts[l], 8], parent / koff int32 [counts[l]].  Same numbering and offset order as cvb200_sc_down_* / _kernel_map. */
+typedef struct cvb200_sc_maps_layout_t {
+    int64_t total_bytes, capacity;
+    int64_t counts, arange, stem_table;
+    int64_t coords[5], keys[5], vals[5], nbr3[5];
+    int64_t children[4], up_table[4], parent[4], koff[4];
+    int64_t flag, scan, cub_temp, cub_temp_bytes;
+} cvb200_sc_maps_layout_t;
+int cvb200_sc_maps_layout(int64_t n, int32_t stem_ksize, int32_t n_down, cvb200_sc_maps_layout_t *layout);
+int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t stem_ksize, int32_t n_down, void *d_workspace,
+                         const cvb200_sc_maps_layout_t *layout, int32_t *h_counts_pinned, void *stream);
+
 /* One fused convolution of an inference program (cvb200_sc_run_program):
  *   out[:, 0:cout) (row stride ldo) = [relu]( sum_k in[table[o,k], 0:cin) (row stride ldi) @ W[k] + bias + residual )
  * `in`, `out` and `residual` may point into column slices of wider buffers (that is how ME.cat,

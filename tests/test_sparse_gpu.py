@@ -270,3 +270,28 @@ def test_persistent_conv_without_split_is_bit_reproducible():
         assert torch.equal(a, b)
     finally:
         L.cvb200_sc_set_conv_options(1, 1)
+
+
+@pytest.mark.parametrize("negative", [False, True])
+def test_fused_map_builder_equals_stepwise_manager(negative):
+    """cvb200_sc_build_maps (one enqueue, one sync, upper-bound allocations, device-side counts) produces exactly the
+    tables of the step-by-step coordinate manager: same coarse numbering, same offset order."""
+    from canonicalvoting_b200.sparse.coords import CoordinateManager
+    coords, _ = _scene(n=6000, G=40, batch=2, seed=21, negative=negative)
+    coords = coords.cuda()
+    ref = CoordinateManager(coords)
+    for ts in (1, 2, 4, 8):
+        ref.down(ts)
+    got = CoordinateManager.build_unet(coords, 5, 4)
+    assert sorted(got.levels) == sorted(ref.levels) == [1, 2, 4, 8, 16]
+    for ts in (1, 2, 4, 8, 16):
+        assert got.levels[ts].n == ref.levels[ts].n
+        assert torch.equal(got.levels[ts].coords, ref.levels[ts].coords)
+        assert torch.equal(got.kernel_map(ts, 3), ref.kernel_map(ts, 3))
+        assert torch.equal(got._nbr[("ident", ts)].view(-1), torch.arange(ref.levels[ts].n, dtype=torch.int32, device="cuda"))
+    assert torch.equal(got.kernel_map(1, 5), ref.kernel_map(1, 5))
+    for ts in (1, 2, 4, 8):
+        for key in ("children", "up_table", "parent", "koff"):
+            assert torch.equal(got.down(ts)[key], ref.down(ts)[key]), (ts, key)
+    # a level built lazily on top of the fused tables (the module path's behaviour) still works: 3^3 map via the stored hash map
+    assert torch.equal(got.kernel_map(2, 1), ref.kernel_map(2, 1))
