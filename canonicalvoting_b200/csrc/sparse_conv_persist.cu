@@ -34,7 +34,7 @@ namespace cvb200 {
 
 constexpr int kPsM = 128, kPsKB = 32, kPsThreads = 320, kPsMaxStages = 8;
 constexpr int kPsSmemBytes = 224 * 1024;                   // of the 227 KiB a CTA may use
-constexpr int kPsMaxSplitTiles = kNumSMs;                    // tiles that can be split in one launch (one partial wave)
+constexpr int kPsMaxSplitTiles = 2 * kNumSMs;                   // tiles that can be split in one launch (one partial wave)
 constexpr size_t kPsScratchFloats = (size_t)kPsMaxSplitTiles * kPsM * 128;
 
 struct PsHeader {
@@ -103,7 +103,7 @@ __device__ __forceinline__ void ps_cp_async_wait(int n) {
 }
 
 // dynamic smem: [header 1 KiB][epilogue staging: 4 warps x 32 rows x 128 B][stages x (A 16 KiB | B nc x 128 B)]
-__global__ void __launch_bounds__(kPsThreads, 1)
+__global__ void __launch_bounds__(kPsThreads, 2)
 sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *__restrict__ in, int ldi, int cout_total,
                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
                        const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P,
@@ -115,6 +115,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool tr = trace != nullptr && blockIdx.x == 0;   // measurement aid: clock64 stamps of the first 256 k-blocks of CTA 0
     int tn = 0;
+    if (tr && tid == 0) trace[3 * 768 + 0] = clock64();
 
     if (tid == 0) {
         for (int s = 0; s < P.stages; s++) {
@@ -136,7 +137,10 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = H.tmem_base;
     // everything above overlapped the previous kernel of the stream; its results are visible after this wait
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tr && tid == 0) trace[3 * 768 + 1] = clock64();
+    // Programmatic dependent launch: everything above overlapped the previous kernel of the stream.  Only what depends
+    // on that kernel waits for it (griddepcontrol.wait, per role): the feature gather and the epilogue (residual, output,
+    // scratch).  The weight tiles and the neighbour ids are static, so their first loads run ahead of the wait.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
@@ -206,38 +210,40 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
     } else if (warp < 6) {
         // ===== gather producers.  A single warp's instruction stream (barrier poll, address arithmetic, copies, arrival)
         // costs ~1000 cycles per k-block whatever the copy count (tools/conv_trace.py), so the four warps do NOT share
-        // a k-block: warp w owns the k-blocks n % 4 == w of the CTA's running k-block sequence and fills their stages
+        // a k-block: warp w owns the k-blocks n % W == w (W = min(4, stages)) of the CTA's running k-block sequence and fills their stages
         // alone -- four k-blocks are being filled at any time.  (n, n + 4 are less than a ring apart, so a warp is never
         // more than one phase ahead of an empty barrier, which is all a parity wait can tell apart.)  Lane (rb, c) copies
         // the 16-byte chunk c of rows rb + 4 j, j < 32; completion arrives on the stage's full barrier by itself
         // (cp.async.mbarrier.arrive.noinc, 32 arrivals per stage), nobody waits for data.
         const int w = warp - 2, c = lane & 7, rb = lane >> 3;
+        const int W = P.stages < 4 ? P.stages : 4;        // producing warps: own k-blocks must be less than a ring apart
         const uint32_t off_even = (uint32_t)(rb * 128 + ((c ^ rb) << 4)), off_odd = (uint32_t)((rb + 4) * 128 + ((c ^ (rb + 4)) << 4));
         const size_t ld4 = (size_t)ldi;
         int n_base = 0;
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
+        bool dep_done = false;
+        for (int u = blockIdx.x; u < P.n_units && w < W; u += gridDim.x) {
             const PsUnit U = ps_unit(P, u);
             // neighbour ids: lane l holds the ids of rows l, l + 32, l + 64, l + 96 for one kernel offset (4 coalesced-ish
             // loads, issued one k-block ahead); the id of row rb + 4 j reaches lane (rb, c) by a shuffle
             const int *nlane = nbr + (size_t)(U.row0 + lane) * k3;
             const int lane_rows = n_out - U.row0 - lane;          // row lane + 32 m exists iff 32 m < lane_rows
             int cur[4], nxt[4];
-            int it = U.kb0 + ((w - n_base) & 3);
+            int it = U.kb0 + (((w - n_base) % W) + W) % W;
             int k_cur = -1, k_nxt = -1;
             if (it < U.kb1) {
                 k_nxt = it / P.cblocks;
 #pragma unroll
                 for (int m = 0; m < 4; m++) nxt[m] = 32 * m < lane_rows ? __ldg(nlane + (size_t)(32 * m) * k3 + k_nxt) : -1;
             }
-            for (; it < U.kb1; it += 4) {
+            for (; it < U.kb1; it += W) {
                 const int k = it / P.cblocks, cb = it - k * P.cblocks;
                 if (k != k_cur) {       // k == k_nxt by construction
 #pragma unroll
                     for (int m = 0; m < 4; m++) cur[m] = nxt[m];
                     k_cur = k;
                 }
-                if (it + 4 < U.kb1) {
-                    const int kn = (it + 4) / P.cblocks;
+                if (it + W < U.kb1) {
+                    const int kn = (it + W) / P.cblocks;
                     if (kn != k_cur) {
 #pragma unroll
                         for (int m = 0; m < 4; m++) nxt[m] = 32 * m < lane_rows ? __ldg(nlane + (size_t)(32 * m) * k3 + kn) : -1;
@@ -246,6 +252,11 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 }
                 const int n = n_base + it - U.kb0;
                 const int round = n / P.stages, s = n - round * P.stages;
+                if (!dep_done) {
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    dep_done = true;
+                    if (tr && tid == 64) trace[3 * 768 + 2] = clock64();
+                }
                 const long long t0 = tr ? clock64() : 0;
                 if (lane == 0) tm_mbar_spin(tm_smem_u32(&H.empty_bar[s]), (uint32_t)((round & 1) ^ 1));
                 __syncwarp();
@@ -271,6 +282,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // ===== epilogue warps 6..9: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
         const int q = warp & 3, et = tid - 192;
         int li = 0;
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
             const int buf = li & 1;
@@ -279,6 +291,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             if (lane == 0 || (P.dbg & 128)) tm_mbar_wait(tm_smem_u32(&H.acc_full[buf]), (uint32_t)((li >> 1) & 1));
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tr && et == 0 && li == 0) trace[3 * 768 + 3] = clock64();
             const int r = U.row0 + q * 32 + lane;
             const uint32_t taddr0 = tmem + (uint32_t)(buf * P.acc_stride) + ((uint32_t)(q * 32) << 16);
             const bool split = U.pieces > 1;
@@ -300,6 +313,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.acc_empty[buf])) : "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tr && et == 0 && li == 0) trace[3 * 768 + 4] = clock64();
                 if (et == 0) {
                     __threadfence();
                     const int old = atomicAdd(counters + U.split_tile, 1);
@@ -309,6 +323,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                     H.last_flag = last;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tr && et == 0 && li == 0) trace[3 * 768 + 5] = clock64();
                 finish = H.last_flag != 0;
             }
             if (finish && (P.nc & 31) == 0) {
@@ -427,8 +442,10 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             }
         }
     }
+    if (tr && tid == 192) trace[3 * 768 + 6] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tr && tid == 0) trace[3 * 768 + 7] = clock64();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
 }
 
@@ -465,7 +482,11 @@ static int ps_workspace(cudaStream_t stream, PsWorkspace *ws) {
     return 0;
 }
 
-static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P) {
+// g_ps_mode: 0 = planner's choice, 1 = deep (one CTA per SM, as many ring stages as fit), 2 = dual (two CTAs per SM with
+// three stages each: two independent pipelines interleave on the SM's tensor core and LSU)
+int g_ps_mode = 0;
+
+static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ctas_per_sm) {
     const int m_tiles = (int)ceil_div(n_out, kPsM);
     int n_splits = 1;
     while (cout / n_splits > 128 || cout % n_splits != 0 || (cout / n_splits) % 16 != 0) n_splits++;
@@ -474,7 +495,11 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P) {
     P->n_tiles = m_tiles * n_splits;
     P->cblocks = cin / kPsKB;
     P->total_kb = k3 * P->cblocks;
-    const int S = kNumSMs;
+    const int stage_bytes = kPsM * 128 + P->nc * 128;
+    const int dual_bytes = 1024 + 16384 + 3 * stage_bytes;
+    const bool dual = g_ps_mode == 2;   // measured slower than the deep ring on every level of the C2 scene (tools/conv_probe.py)
+    *ctas_per_sm = (dual && dual_bytes <= 115712) ? 2 : 1;
+    const int S = kNumSMs * *ctas_per_sm;
     P->n_whole = (P->n_tiles / S) * S;
     const int R = P->n_tiles - P->n_whole;
     int best_ks = 1;
@@ -491,16 +516,18 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P) {
     if (((g_ps_debug >> 8) & 255) > 0 && R > 0) best_ks = ((g_ps_debug >> 8) & 255) < P->total_kb ? ((g_ps_debug >> 8) & 255) : P->total_kb;   // probe override
     P->ks = best_ks;
     if (best_ks == 1) P->n_whole = P->n_tiles;
+    if (P->n_tiles - P->n_whole > kPsMaxSplitTiles) {   // cannot happen with S <= 2 * kNumSMs and the scratch sized for it; be safe
+        P->ks = 1;
+        P->n_whole = P->n_tiles;
+    }
     P->n_units = P->n_whole + (P->n_tiles - P->n_whole) * P->ks;
-    const int stage_bytes = kPsM * 128 + P->nc * 128;
     int stages = (kPsSmemBytes - 1024 - 16384) / stage_bytes;
-    P->stages = stages > kPsMaxStages ? kPsMaxStages : stages;
+    P->stages = *ctas_per_sm == 2 ? 3 : (stages > kPsMaxStages ? kPsMaxStages : stages);
     int cols = 32;
     while (cols < 2 * P->nc) cols <<= 1;
     P->tmem_cols = cols;
     P->acc_stride = cols / 2;
     P->dbg = g_ps_debug & 0xff00ff;
-
 }
 
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
@@ -515,7 +542,8 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
                   reinterpret_cast<uintptr_t>(d_res)) & 15) == 0 && ldi % 4 == 0 && ldo % 4 == 0 && ldr % 4 == 0,
                 CVB200_EINVAL, "sc_conv_forward_tc: 16-byte aligned pointers and row strides required");
     PsPlan P;
-    ps_plan(n_out, cin, cout, k3, &P);
+    int ctas_per_sm = 1;
+    ps_plan(n_out, cin, cout, k3, &P, &ctas_per_sm);
     PsWorkspace ws;
     if (int rc = ps_workspace(stream, &ws)) return rc;
     alignas(64) CUtensorMap map_b;
@@ -527,7 +555,8 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
         set = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(P.n_units < kNumSMs ? P.n_units : kNumSMs));
+    const int slots = kNumSMs * ctas_per_sm;
+    cfg.gridDim = dim3((unsigned)(P.n_units < slots ? P.n_units : slots));
     cfg.blockDim = dim3(kPsThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -546,6 +575,12 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
 extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) {
     cvb200::g_ps_allow_split = allow_split != 0;
     cvb200::g_ps_use_pdl = use_pdl != 0;
+    return 0;
+}
+
+extern "C" int cvb200_sc_set_conv_mode(int32_t mode) {
+    CVB_REQUIRE(mode >= 0 && mode <= 2, CVB200_EINVAL, "sc_set_conv_mode: 0 (planner), 1 (deep ring, one CTA per SM) or 2 (two CTAs per SM)");
+    cvb200::g_ps_mode = mode;
     return 0;
 }
 

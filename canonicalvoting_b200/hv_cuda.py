@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 _work_cache = {}       # (device index, stream id) -> zero-filled workspace tensor
-_dims_work = {}        # device index -> small scratch for the min/max reduction
+_dims_work = {}        # (device index, stream id) -> small scratch for the min/max reduction
 
 
 def _check_input(t, name):
@@ -64,7 +64,7 @@ def grid_dims(points, res):
     """(corner[3], maxpt[3], dims[3]) python tuples; the reference's float32 host arithmetic
     (hv_cuda_kernel.cu:129-134).  Synchronises the current stream once."""
     L = _lib.load()
-    dev = points.device.index
+    dev = (points.device.index, torch.cuda.current_stream(points.device).cuda_stream)   # per stream: callers may run concurrently
     work = _dims_work.get(dev)
     if work is None:
         work = torch.empty(L.cvb200_hv_grid_dims_work_bytes(), dtype=torch.uint8, device=points.device)

@@ -50,15 +50,16 @@ cases_all = [("L1 3^3 96->96", cm.kernel_map(1, 3), cm.levels[1].n, 96, 96),
          ("L8 3^3 256->256", cm.kernel_map(8, 3), cm.levels[8].n, 256, 256),
          ("L16 3^3 256->256", cm.kernel_map(16, 3), cm.levels[16].n, 256, 256),
          ("L1 up 2^3 96->96", cm._down[1]["up_table"], cm.levels[2].n, 96, 96)]
-cases = cases_all[:1] + cases_all[2:3] + cases_all[5:6]
-modes = [(0, "normal"), (32, "all lanes poll"), (13, "barriers only"), (13 + 32, "barriers only, all lanes poll")]
+cases = cases_all
+modes = [(0, "deep"), (-2, "dual")]
 for impl in (3,):
     L.cvb200_sc_set_conv_impl(impl)
     for name, table, n_in, cin, cout in cases:
         pairs = int((table >= 0).sum())
         line = "impl %d %-18s rows %6d pairs %8d:" % (impl, name, table.shape[0], pairs)
         for mask, label in (modes if impl == 3 else modes[:1]):
-            L.cvb200_sc_set_conv_debug(mask)
+            L.cvb200_sc_set_conv_mode(2 if mask == -2 else 1)
+            L.cvb200_sc_set_conv_debug(max(mask, 0))
             us = run(table, n_in, cin, cout)
             line += "  %s %.1f us" % (label, us)
             if mask == 0:
