@@ -54,7 +54,7 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index, period_ms=100):
+    def __init__(self, gpu_index, period_ms=50):
         self.idx, self.period, self.samples, self.proc = gpu_index, period_ms, [], None
 
     def start(self):
