@@ -12,6 +12,7 @@ num_rots = 12.  Prints ONE JSON line (rank 0).  DESIGN.md "Measurement" defines 
                timed steps, max over ranks
   e2e          scenes/s through the reference-facing API starting from pinned HOST buffers: H2D of coords + feats ->
                engine -> decode -> hv_cuda.forward (with its geometry sync) -> D2H of the step's result
+  passes       the K-step loop runs three times back to back; `value` is the median pass, all three are in passes_ms_per_step
   roofline     the dominant kernel group of the step = the tcgen05 sparse-convolution program of the U-Net:
                algorithmic FLOPs 2 * sum(pairs * cin * cout) / its CUDA-event time, against the measured dense
                tensor peak; `vote` holds the HBM roofline of the vote op (40 N + 24 G bytes)
@@ -421,7 +422,7 @@ def main():
         t_e2e = min(t_e2e, run_lanes(run_e2e, args.steps))
         barrier()
     h2d = coords_h.numel() * 4 + feats_h.numel() * 4
-    d2h = 8 + 4 * 4                                    # result + the per-level voxel counts the coordinate manager reads
+    d2h = 8 + 4 * 5 + 36                               # result + the level sizes of the map builder + the vote grid geometry (hv_cuda.forward)
 
     # ---- max over ranks
     times = torch.tensor([t_resident, t_e2e], dtype=torch.float64, device=dev)
@@ -467,10 +468,12 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (U-Net) / f32 (vote)",
             "data": "synthetic", "config": dict(workload_config(args.workload, sc), scenes_in_flight_per_gpu=n_streams),
             "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": (len(arr) + 77) * args.steps,   # 63 conv ops + finish passes, coordinate-map kernels, decode, vote (ncu launch list: 140 of ours per step)
+            # per step: the convolution program (63 persistent conv launches + im2col), 29 kernels of the fused map builder
+            # (csrc/sparse_maps.cu), head decode, vote scatter + write-out  (ncu launch list: profiles/r1s_launches_bench_C2.csv)
+            "gpu_launches": (len(arr) + 29 + 3) * args.steps,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
                          "traffic": None, "peak_source": peak_src + ": bf16 sustained / 2 (kind::tf32 runs at half the bf16 rate)",
-                         "kernel": "sc_conv_tc_kernel program of the U-Net (%d fused conv ops incl. stem and finish passes)" % len(arr),
+                         "kernel": "sc_conv_persist_kernel program of the U-Net (%d launches: 63 fused convolutions + the stem's im2col)" % len(arr),
                          "algorithmic_flops": flops, "kernel_ms": unet_med,
                          "vote": {"bound": "hbm", "achieved": vote_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": vote_gbs / hbm_gbs,
                                   "kernel": "hv_scatter_kernel + hv_finalize_kernel", "algorithmic_bytes": vbytes,
