@@ -59,7 +59,6 @@ SIGNATURES.update({
     "cvb200_sc_set_conv_impl": (ctypes.c_int, [_i32]),
     "cvb200_sc_set_conv_options": (ctypes.c_int, [_i32, _i32]),
     "cvb200_sc_set_conv_debug": (ctypes.c_int, [_i32]),
-    "cvb200_sc_set_conv_mode": (ctypes.c_int, [_i32]),
     "cvb200_sc_set_conv_trace": (ctypes.c_int, [_vp]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
 })

@@ -10,10 +10,11 @@
 //   * ONE CTA per SM walks a list of work units.  A unit = (row tile of 128 outputs, channel split, piece of the
 //     k-block sequence); the host plans whole tiles for the full waves and cuts the tiles of the last, partial wave
 //     (or all tiles of a small level) into `ks` pieces so that every SM gets the same amount of k-blocks.
-//   * roles: warp 0 = weight-tile TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-5 = gather
+//   * roles: warp 0 = weight-tile TMA producer, warps 1 and 12 = MMA issuers (alternating k-blocks; warp 1 owns the TMEM
+//     allocation), warps 2-7 = gather
 //     producers (16-byte cp.async straight from the feature matrix into the 128B-swizzled A tile, zero-length copy =
 //     zero fill for a missing neighbour; neighbour ids are read from the table one offset ahead, no staging pass),
-//     warps 6-9 = epilogue.  full/empty mbarriers per ring stage (up to 8 stages, ~200 KB of shared memory).
+//     warps 8-11 = epilogue.  full/empty mbarriers per ring stage (up to 8 stages, ~200 KB of shared memory).
 //   * TWO accumulators in tensor memory: the epilogue of unit i (tcgen05.ld -> bias/residual/ReLU -> global) runs
 //     while the MMA warp already accumulates unit i+1.
 //   * pieces of a split tile add their partial sums into a zero-initialised, self-cleaning scratch tile
@@ -32,13 +33,15 @@
 
 namespace cvb200 {
 
-constexpr int kPsM = 128, kPsKB = 32, kPsThreads = 320, kPsMaxStages = 8;
+constexpr int kPsM = 128, kPsKB = 32, kPsThreads = 416, kPsMaxStages = 8;
+constexpr int kPsProducers = 4;   // gather warps 1,2,3,5 (6,7 too when set to 6: measured slower); TMA warp 0; MMA issuers 4 and 12 (same
+                                  // scheduler as warp 0); epilogue warps 8..11
 constexpr int kPsSmemBytes = 224 * 1024;                   // of the 227 KiB a CTA may use
 constexpr int kPsMaxSplitTiles = 2 * kNumSMs;                   // tiles that can be split in one launch (one partial wave)
 constexpr size_t kPsScratchFloats = (size_t)kPsMaxSplitTiles * kPsM * 128;
 
 struct PsHeader {
-    unsigned long long full_bar[kPsMaxStages], empty_bar[kPsMaxStages], acc_full[2], acc_empty[2];
+    unsigned long long full_bar[kPsMaxStages], empty_bar[kPsMaxStages], acc_full[2], acc_empty[2], turn[2];
     unsigned int tmem_base;
     int last_flag;
 };
@@ -103,7 +106,7 @@ __device__ __forceinline__ void ps_cp_async_wait(int n) {
 }
 
 // dynamic smem: [header 1 KiB][epilogue staging: 4 warps x 32 rows x 128 B][stages x (A 16 KiB | B nc x 128 B)]
-__global__ void __launch_bounds__(kPsThreads, 2)
+__global__ void __launch_bounds__(kPsThreads, 1)
 sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *__restrict__ in, int ldi, int cout_total,
                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
                        const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P,
@@ -123,12 +126,13 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
-            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), 1);
+            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), 2);      // both MMA warps
             tm_mbar_init(tm_smem_u32(&H.acc_empty[b]), 4);
+            tm_mbar_init(tm_smem_u32(&H.turn[b]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tm_smem_u32(&H.tmem_base)), "r"(P.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -172,51 +176,70 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 if (++cb == P.cblocks) { cb = 0; k++; }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform loop, one elected lane issues; accumulator (li & 1) in tensor memory
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.nc >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
-        int s = 0, li = 0;
-        uint32_t ph = 0;
+    } else if (warp == 4 || warp == 12) {
+        // ===== MMA issuers: TWO warps, k-block n of the CTA's running sequence belongs to warp n & 1.  One warp's
+        // per-k-block protocol (poll the full barrier, proxy fence, four tcgen05.mma, commit, loop) takes longer than the
+        // tensor core needs for the k-block, so a single issuer bounded the kernel ("barriers only": 66 of 90 us); with two,
+        // one warp's hand-shake overlaps the other's MMAs.  The MMAs themselves are issued in strict sequence (a `turn`
+        // barrier per warp, handed over right after the four MMAs of a k-block): the tensor pipe executes in issue
+        // order, stages are released in order, and the first k-block of a unit overwrites the accumulator before anything
+        // is added to it.  Both warps commit to acc_full (count 2).
+        const int me = warp == 4 ? 0 : 1;
+        int li = 0, n_base = 0;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.nc >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
             const int buf = li & 1;
-            tm_mbar_wait(tm_smem_u32(&H.acc_empty[buf]), (uint32_t)(((li >> 1) & 1) ^ 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int first = U.kb0 + ((me - n_base) & 1);        // my first k-block of this unit
             const uint32_t d_tmem = tmem + (uint32_t)(buf * P.acc_stride);
-            for (int it = U.kb0; it < U.kb1; it++) {
-                const long long t0 = tr ? clock64() : 0;
-                tm_mbar_wait(tm_smem_u32(&H.full_bar[s]), ph);
-                if (tr && lane == 0 && tn < 256) { trace[3 * tn] = t0; trace[3 * tn + 1] = clock64(); }
+            if (first == U.kb0 && first < U.kb1) {
+                tm_mbar_wait(tm_smem_u32(&H.acc_empty[buf]), (uint32_t)(((li >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            for (int it = first; it < U.kb1; it += 2) {
+                const int n = n_base + it - U.kb0;
+                const int round = n / P.stages, s = n - round * P.stages;
+                const long long t0 = tr ? clock64() : 0;
+                tm_mbar_wait(tm_smem_u32(&H.full_bar[s]), (uint32_t)(round & 1));
+                if (tr && me == 0 && lane == 0 && tn < 256) { trace[3 * tn] = t0; trace[3 * tn + 1] = clock64(); }
                 const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
                 const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
+                if (!(P.dbg & 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
+                // my turn: the other warp has issued k-block n - 1
+                if (n > 0) tm_mbar_wait(tm_smem_u32(&H.turn[me]), (uint32_t)(((n >> 1) + me + 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tm_elect_one()) {
-                    if (!(P.dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
                     if (!(P.dbg & 4)) {
 #pragma unroll
                         for (int kk = 0; kk < kPsKB / 8; kk++)
                             tm_umma_tf32(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > U.kb0 || kk > 0) ? 1u : 0u);
                     }
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.turn[me ^ 1])) : "memory");
                     tm_commit(tm_smem_u32(&H.empty_bar[s]));
                 }
                 __syncwarp();
-                if (tr && lane == 0 && tn < 256) { trace[3 * tn + 2] = clock64(); }
+                if (tr && me == 0 && lane == 0 && tn < 256) { trace[3 * tn + 2] = clock64(); }
                 tn++;
-                if (++s == P.stages) { s = 0; ph ^= 1u; }
             }
-            if (tm_elect_one()) tm_commit(tm_smem_u32(&H.acc_full[buf]));
+            if (tm_elect_one()) {
+                if (first < U.kb1) tm_commit(tm_smem_u32(&H.acc_full[buf]));       // arrives when my MMAs of the unit are complete
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.acc_full[buf])) : "memory");
+            }
             __syncwarp();
+            n_base += U.kb1 - U.kb0;
         }
-    } else if (warp < 6) {
+    } else if (warp < 8) {
         // ===== gather producers.  A single warp's instruction stream (barrier poll, address arithmetic, copies, arrival)
-        // costs ~1000 cycles per k-block whatever the copy count (tools/conv_trace.py), so the four warps do NOT share
+        // costs ~1000 cycles per k-block whatever the copy count (tools/conv_trace.py), so the gather warps do NOT share
         // a k-block: warp w owns the k-blocks n % W == w (W = min(4, stages)) of the CTA's running k-block sequence and fills their stages
-        // alone -- four k-blocks are being filled at any time.  (n, n + 4 are less than a ring apart, so a warp is never
+        // alone -- W k-blocks are being filled at any time.  (n, n + W are less than a ring apart, so a warp is never
         // more than one phase ahead of an empty barrier, which is all a parity wait can tell apart.)  Lane (rb, c) copies
         // the 16-byte chunk c of rows rb + 4 j, j < 32; completion arrives on the stage's full barrier by itself
         // (cp.async.mbarrier.arrive.noinc, 32 arrivals per stage), nobody waits for data.
-        const int w = warp - 2, c = lane & 7, rb = lane >> 3;
-        const int W = P.stages < 4 ? P.stages : 4;        // producing warps: own k-blocks must be less than a ring apart
+        // warp placement: a scheduler (warp % 4) that hosts an MMA issuer or the TMA warp hosts no gather warp, whose long
+        // instruction streams would delay the issuers' latency-critical hand-shakes
+        const int w = warp < 4 ? warp - 1 : warp - 2, c = lane & 7, rb = lane >> 3;   // warps 1,2,3,5,6,7 -> 0..5
+        const int W = P.stages < kPsProducers ? P.stages : kPsProducers;   // producing warps: own k-blocks must be less than a ring apart
         const uint32_t off_even = (uint32_t)(rb * 128 + ((c ^ rb) << 4)), off_odd = (uint32_t)((rb + 4) * 128 + ((c ^ (rb + 4)) << 4));
         const size_t ld4 = (size_t)ldi;
         int n_base = 0;
@@ -255,12 +278,12 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 if (!dep_done) {
                     asm volatile("griddepcontrol.wait;" ::: "memory");
                     dep_done = true;
-                    if (tr && tid == 64) trace[3 * 768 + 2] = clock64();
+                    if (tr && tid == 32) trace[3 * 768 + 2] = clock64();
                 }
                 const long long t0 = tr ? clock64() : 0;
                 if (lane == 0) tm_mbar_spin(tm_smem_u32(&H.empty_bar[s]), (uint32_t)((round & 1) ^ 1));
                 __syncwarp();
-                if (tr && tid == 64 && tn < 256) { trace[768 + 3 * tn] = t0; trace[768 + 3 * tn + 1] = clock64(); }
+                if (tr && tid == 32 && tn < 256) { trace[768 + 3 * tn] = t0; trace[768 + 3 * tn + 1] = clock64(); }
                 const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes);
                 const float *src0 = in + c * 4 + cb * kPsKB;
 #pragma unroll
@@ -272,15 +295,15 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(id >= 0 ? 16u : 0u) : "memory");
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
-                if (tr && tid == 64 && tn < 256) { trace[768 + 3 * tn + 2] = clock64(); }
+                if (tr && tid == 32 && tn < 256) { trace[768 + 3 * tn + 2] = clock64(); }
                 tn++;
             }
             (void)k_nxt;
             n_base += U.kb1 - U.kb0;
         }
     } else {
-        // ===== epilogue warps 6..9: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
-        const int q = warp & 3, et = tid - 192;
+        // ===== epilogue warps 8..11: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
+        const int q = warp & 3, et = tid - 256;
         int li = 0;
         asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
@@ -442,11 +465,11 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             }
         }
     }
-    if (tr && tid == 192) trace[3 * 768 + 6] = clock64();
+    if (tr && tid == 256) trace[3 * 768 + 6] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tr && tid == 0) trace[3 * 768 + 7] = clock64();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------- host side
@@ -482,9 +505,6 @@ static int ps_workspace(cudaStream_t stream, PsWorkspace *ws) {
     return 0;
 }
 
-// g_ps_mode: 0 = planner's choice, 1 = deep (one CTA per SM, as many ring stages as fit), 2 = dual (two CTAs per SM with
-// three stages each: two independent pipelines interleave on the SM's tensor core and LSU)
-int g_ps_mode = 0;
 
 static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ctas_per_sm) {
     const int m_tiles = (int)ceil_div(n_out, kPsM);
@@ -497,8 +517,10 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ct
     P->total_kb = k3 * P->cblocks;
     const int stage_bytes = kPsM * 128 + P->nc * 128;
     const int dual_bytes = 1024 + 16384 + 3 * stage_bytes;
-    const bool dual = g_ps_mode == 2;   // measured slower than the deep ring on every level of the C2 scene (tools/conv_probe.py)
-    *ctas_per_sm = (dual && dual_bytes <= 115712) ? 2 : 1;
+    // two CTAs per SM with 3-stage rings were measured slower than one deep ring on every level (113 vs 91 us on the large
+    // layers) and are no longer offered; the register budget is now spent on one CTA
+    (void)dual_bytes;
+    *ctas_per_sm = 1;
     const int S = kNumSMs * *ctas_per_sm;
     P->n_whole = (P->n_tiles / S) * S;
     const int R = P->n_tiles - P->n_whole;
@@ -578,11 +600,6 @@ extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) 
     return 0;
 }
 
-extern "C" int cvb200_sc_set_conv_mode(int32_t mode) {
-    CVB_REQUIRE(mode >= 0 && mode <= 2, CVB200_EINVAL, "sc_set_conv_mode: 0 (planner), 1 (deep ring, one CTA per SM) or 2 (two CTAs per SM)");
-    cvb200::g_ps_mode = mode;
-    return 0;
-}
 
 /* Measurement aid: switch off parts of the persistent kernel (results become garbage): 1 no gather copies, 2 no zero-fill
  * copies, 4 no MMA, 8 no weight TMA.  0 = normal operation. */

@@ -188,9 +188,6 @@ int cvb200_sc_set_conv_impl(int32_t impl);
 /* Options of implementation 3.  allow_split = 0: never cut a tile into pieces (no float atomics: bit-reproducible
  * results; slower on small levels).  use_pdl = 0: no programmatic dependent launch.  Defaults: 1, 1. */
 int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl);
-/* Occupancy of implementation 3: 0 = planner's choice (default), 1 = one CTA per SM with a deep ring (7-8 stages),
- * 2 = two CTAs per SM with three stages each. */
-int cvb200_sc_set_conv_mode(int32_t mode);
 
 /* Measurement aid (tools/conv_probe.py): switch off parts of implementation 3 to find which side bounds it -- results are
  * garbage while mask != 0.  1 = no gather copies, 2 = no zero-fill copies, 4 = no MMA, 8 = no weight TMA. */

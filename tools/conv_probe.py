@@ -50,15 +50,14 @@ cases_all = [("L1 3^3 96->96", cm.kernel_map(1, 3), cm.levels[1].n, 96, 96),
          ("L8 3^3 256->256", cm.kernel_map(8, 3), cm.levels[8].n, 256, 256),
          ("L16 3^3 256->256", cm.kernel_map(16, 3), cm.levels[16].n, 256, 256),
          ("L1 up 2^3 96->96", cm._down[1]["up_table"], cm.levels[2].n, 96, 96)]
-cases = cases_all
-modes = [(0, "deep"), (-2, "dual")]
+cases = cases_all[:1] + cases_all[2:3] + cases_all[4:5]
+modes = [(0, "normal"), (13, "barriers only"), (1, "no gather"), (4, "no MMA"), (8, "no weight TMA")]
 for impl in (3,):
     L.cvb200_sc_set_conv_impl(impl)
     for name, table, n_in, cin, cout in cases:
         pairs = int((table >= 0).sum())
         line = "impl %d %-18s rows %6d pairs %8d:" % (impl, name, table.shape[0], pairs)
         for mask, label in (modes if impl == 3 else modes[:1]):
-            L.cvb200_sc_set_conv_mode(2 if mask == -2 else 1)
             L.cvb200_sc_set_conv_debug(max(mask, 0))
             us = run(table, n_in, cin, cout)
             line += "  %s %.1f us" % (label, us)
