@@ -61,6 +61,7 @@ SIGNATURES.update({
     "cvb200_sc_set_conv_debug": (ctypes.c_int, [_i32]),
     "cvb200_sc_set_conv_trace": (ctypes.c_int, [_vp]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
+    "cvb200_sc_conv_wgrad_tc": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _vp]),
 })
 
 

@@ -141,8 +141,9 @@ __device__ __forceinline__ void tm_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 2-D fp32 tensor map with SWIZZLE_128B (defined in sparse_conv_tma.cu); returns a cvb200 status
+// 2-D fp32 tensor map with SWIZZLE_128B, or its 32-byte-atom variant that MN-major tf32 operands need (defined in
+// sparse_conv_tma.cu); returns a cvb200 status
 int make_map_2d(CUtensorMap *m, const float *base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
-                uint32_t box_rows);
+                uint32_t box_rows, int swizzle_atom_32b = 0);
 
 }  // namespace cvb200

@@ -178,6 +178,12 @@ int cvb200_sc_conv_forward(const float *d_in, int32_t cin, const float *d_w, int
 int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_t cin, const float *d_wt, int32_t cout, const int32_t *d_nbr,
                               int64_t n_out, int32_t k3, const float *d_bias, float *d_out, void *stream);
 
+/* Weight gradient on the tensor cores (csrc/sparse_wgrad_tc.cu): dW [k3, cin, cout] = sum_o x[table[o,k]]^T (x) dout[o], the
+ * contraction over rows as tcgen05 kind::tf32 MMAs with MN-major operands, fp32 accumulation in tensor memory, partial
+ * tiles combined with float atomics.  Needs cin % 32 == 0, cout % 32 == 0, cout <= 256; x row stride = cin. */
+int cvb200_sc_conv_wgrad_tc(const float *d_x, int32_t cin, const float *d_dout, int32_t cout, const int32_t *d_table,
+                            int64_t n_rows, int32_t k3, float *d_dw, void *stream);
+
 /* Implementation of the tensor-core convolution (all compute the same contraction; selectable for A/B measurements):
  * 3 = persistent warp-specialised kernel: one CTA per SM walks work units, two accumulators in tensor memory, tiles of
  *     the partial wave / of small levels are cut into pieces whose partial sums are combined in-kernel (default);

@@ -295,3 +295,44 @@ def test_fused_map_builder_equals_stepwise_manager(negative):
             assert torch.equal(got.down(ts)[key], ref.down(ts)[key]), (ts, key)
     # a level built lazily on top of the fused tables (the module path's behaviour) still works: 3^3 map via the stored hash map
     assert torch.equal(got.kernel_map(2, 1), ref.kernel_map(2, 1))
+
+
+@pytest.mark.parametrize("cin,cout,k3", [(32, 32, 27), (96, 96, 27), (128, 96, 27), (64, 128, 8), (256, 256, 27), (384, 256, 1), (192, 128, 27)])
+def test_tensor_core_wgrad_matches_fp32_kernel(cin, cout, k3):
+    """tcgen05 weight gradient (MN-major tf32 operands, rows as the contraction dimension) vs the fp32 CUDA-core kernel."""
+    from canonicalvoting_b200.sparse.functional import conv_wgrad
+    g = torch.Generator().manual_seed(cin + cout + k3)
+    n_in, n_out = 5000, 4100                      # 4100 rows: a ragged last 32-row stage
+    table = torch.randint(-1, n_in, (n_out, k3), generator=g, dtype=torch.int64).int()
+    table[torch.rand(n_out, k3, generator=g) < 0.5] = -1
+    x = torch.randn(n_in, cin, generator=g).cuda()
+    dout = torch.randn(n_out, cout, generator=g).cuda()
+    ref = conv_wgrad(x, dout, table.cuda(), mode="fp32")
+    got = conv_wgrad(x, dout, table.cuda(), mode="tf32")
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert got.shape == ref.shape == (k3, cin, cout)
+    assert err <= 3e-3 * scale, "cin=%d cout=%d k3=%d: max err %.3e vs scale %.3e" % (cin, cout, k3, err, scale)
+    assert err > 0
+
+
+def test_small_width_conv_im2col_path_forward_and_wgrad():
+    """3-channel 5^3 stem in tf32 mode: im2col + tensor-core product / tensor-core weight gradient == the fp32 kernels."""
+    from canonicalvoting_b200 import sparse as ME
+    coords, feats = _scene(n=3000, G=24, batch=2, cin=3, seed=5)
+    torch.manual_seed(2)
+    conv = ME.MinkowskiConvolution(3, 32, kernel_size=5, dimension=3).cuda()
+    out = {}
+    for mode in ("fp32", "tf32"):
+        ME.set_forward_mode(mode)
+        try:
+            conv.zero_grad()
+            y = conv(ME.SparseTensor(feats, coords, device="cuda")).F
+            (y * torch.linspace(-1, 1, y.numel(), device="cuda").view_as(y)).sum().backward()
+            out[mode] = (y.detach().clone(), conv.kernel.grad.detach().clone())
+        finally:
+            ME.set_forward_mode("fp32")
+    for a, b, what in zip(out["tf32"], out["fp32"], ("forward", "dW")):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 3e-3 * float(b.abs().max()), what
