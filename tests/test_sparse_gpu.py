@@ -336,3 +336,35 @@ def test_small_width_conv_im2col_path_forward_and_wgrad():
     for a, b, what in zip(out["tf32"], out["fp32"], ("forward", "dW")):
         assert a.shape == b.shape
         assert float((a - b).abs().max()) <= 3e-3 * float(b.abs().max()), what
+
+
+def test_edge_cases_tiny_inputs():
+    """One-row convolutions, fewer rows than a 32-row stage in the weight gradient, a 10-voxel scene through the fused
+    map builder and the engine (levels shrink to a single voxel)."""
+    from canonicalvoting_b200.engine import MinkUNetEngine
+    from canonicalvoting_b200.minkunet import MinkUNet34C
+    from canonicalvoting_b200.sparse.coords import CoordinateManager
+    from canonicalvoting_b200.sparse.functional import conv_table_forward, conv_wgrad
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(7, 64, generator=g).cuda()
+    w = torch.randn(27, 64, 32, generator=g).cuda() * 0.1
+    table = torch.randint(-1, 7, (1, 27), generator=g, dtype=torch.int64).int().cuda()
+    ref = conv_table_forward(x, w, table, None, mode="fp32")
+    got = conv_table_forward(x, w, table, None, mode="tf32")
+    assert float((got - ref).abs().max()) <= 3e-3 * max(float(ref.abs().max()), 1e-6)
+    table = torch.randint(-1, 7, (5, 27), generator=g, dtype=torch.int64).int().cuda()
+    dout = torch.randn(5, 32, generator=g).cuda()
+    rw, gw = conv_wgrad(x, dout, table, mode="fp32"), conv_wgrad(x, dout, table, mode="tf32")
+    assert float((gw - rw).abs().max()) <= 3e-3 * max(float(rw.abs().max()), 1e-6)
+    empty = conv_wgrad(x, dout[:0], table[:0], mode="tf32")
+    assert empty.shape == (27, 64, 32) and float(empty.abs().max()) == 0.0
+    coords = torch.tensor([[0, i, (3 * i) % 7, (5 * i) % 11] for i in range(10)], dtype=torch.int32).cuda()
+    ref_cm = CoordinateManager(coords)
+    for ts in (1, 2, 4, 8):
+        ref_cm.down(ts)
+    cm = CoordinateManager.build_unet(coords, 5, 4)
+    assert [cm.levels[ts].n for ts in (1, 2, 4, 8, 16)] == [ref_cm.levels[ts].n for ts in (1, 2, 4, 8, 16)]
+    torch.manual_seed(0)
+    model = MinkUNet34C(3, 64).cuda().eval()
+    out = MinkUNetEngine(model)(coords, torch.rand(10, 3).cuda())
+    assert out.shape == (10, 64) and torch.isfinite(out).all()
