@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kPsThreads, 1)
 sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *__restrict__ in, int ldi, int cout_total,
                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
                        const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P,
-                       float *__restrict__ scratch, int *__restrict__ counters, long long *__restrict__ trace) {
+                       float *__restrict__ scratch, int *__restrict__ counters, long long *__restrict__ trace, int g4) {
     extern __shared__ __align__(1024) unsigned char smem[];
     PsHeader &H = *reinterpret_cast<PsHeader *>(smem);
     unsigned char *stage0 = smem + 1024 + 16384;       // [header 1 KiB][epilogue staging 4 x 4 KiB][ring]
@@ -253,7 +253,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             int cur[4], nxt[4];
             int it = U.kb0 + (((w - n_base) % W) + W) % W;
             int k_cur = -1, k_nxt = -1;
-            if (it < U.kb1) {
+            if (it < U.kb1 && !g4) {
                 k_nxt = it / P.cblocks;
 #pragma unroll
                 for (int m = 0; m < 4; m++) nxt[m] = 32 * m < lane_rows ? __ldg(nlane + (size_t)(32 * m) * k3 + k_nxt) : -1;
@@ -265,7 +265,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                     for (int m = 0; m < 4; m++) cur[m] = nxt[m];
                     k_cur = k;
                 }
-                if (it + W < U.kb1) {
+                if (it + W < U.kb1 && !g4) {
                     const int kn = (it + W) / P.cblocks;
                     if (kn != k_cur) {
 #pragma unroll
@@ -285,6 +285,21 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 __syncwarp();
                 if (tr && tid == 32 && tn < 256) { trace[768 + 3 * tn] = t0; trace[768 + 3 * tn + 1] = clock64(); }
                 const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes);
+                if (g4) {
+                    // 4-channel input (the padded 3-channel stem): the k-block's 32 "channels" are 8 neighbours x 4 channels, chunk
+                    // c of row r is the 16-byte feature vector of neighbour 8 cb + c -- the im2col matrix is never materialised
+                    const int col = 8 * cb + c;
+                    int ids[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        ids[j] = (col < g4 && U.row0 + rb + 4 * j < n_out) ? __ldg(nbr + (size_t)(U.row0 + rb + 4 * j) * g4 + col) : -1;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float *src = in + (size_t)(ids[j] >= 0 ? ids[j] : 0) * ld4;
+                        const uint32_t dst = a_s + ((j & 1) ? off_odd : off_even) + (uint32_t)((j >> 1) * 1024);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ids[j] >= 0 ? 16u : 0u) : "memory");
+                    }
+                } else {
                 const float *src0 = in + c * 4 + cb * kPsKB;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
@@ -293,6 +308,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                     const uint32_t dst = a_s + ((j & 1) ? off_odd : off_even) + (uint32_t)((j >> 1) * 1024);
                     if (!(P.dbg & 1))
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(id >= 0 ? 16u : 0u) : "memory");
+                }
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
                 if (tr && tid == 32 && tn < 256) { trace[768 + 3 * tn + 2] = clock64(); }
@@ -552,9 +568,13 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ct
     P->dbg = g_ps_debug & 0xff00ff;
 }
 
+// g4 > 0: `d_in` has 4 channels per row (ldi = 4), `d_nbr` is a table [n_out][g4] and the contraction runs over
+// K = 32 * ceil(g4 / 8) = (neighbour, channel) pairs; cin must be that K, k3 must be 1, d_wt = [cout][K]
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int g4) {
+    CVB_REQUIRE(g4 == 0 || (k3 == 1 && ldi == 4 && cin == 32 * ((g4 + 7) / 8)), CVB200_EINVAL,
+                "sc_conv (4-channel gather): needs k3 == 1, ldi == 4, cin == 32 * ceil(width / 8) (got %d, %d, %d for width %d)", k3, ldi, cin, g4);
     CVB_REQUIRE(cin > 0 && cin % kPsKB == 0 && cout >= 16 && cout <= 1024 && cout % 16 == 0 && k3 > 0, CVB200_EINVAL,
                 "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout (got %d, %d, %d)", cin, cout, k3);
     CVB_REQUIRE(n_out >= 0 && n_out < (1LL << 31) && n_in > 0 && n_in < (1LL << 31), CVB200_EINVAL, "sc_conv_forward_tc: bad n_out / n_in");
@@ -588,7 +608,7 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     cfg.attrs = attr;
     cfg.numAttrs = g_ps_use_pdl ? 1 : 0;
     CVB_CUDA(cudaLaunchKernelEx(&cfg, sc_conv_persist_kernel, map_b, d_in, ldi, cout, (const int *)d_nbr, (int)n_out, k3, d_bias, d_res,
-                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace));
+                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace, g4));
     return 0;
 }
 

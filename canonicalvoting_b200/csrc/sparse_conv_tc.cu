@@ -279,7 +279,7 @@ int launch_conv_tma(int gather_a, const float *d_in, int64_t n_in, int ldi, int 
                     cudaStream_t stream);
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int g4 = 0);
 // 3: persistent warp-specialised kernel, two TMEM accumulators, split tiles reduced in-kernel (sparse_conv_persist.cu);
 // 2: warp-specialised kernel, one tile per CTA, A by cp.async producers + B by TMA (sparse_conv_tma.cu); 1: same kernel, A by
 // TMA gather4; 0: cp.async kernel with a CTA-wide barrier per k-block (this file)

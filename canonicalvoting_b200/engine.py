@@ -19,6 +19,7 @@ compat package) into a flat program of fused convolution ops executed back to ba
 """
 import collections
 import ctypes
+import os
 
 import torch
 
@@ -103,6 +104,7 @@ class MinkUNetEngine:
         self._pool = None                     # one worker thread for prefetch()
         self._pinned = None                   # count read-back buffer of the fused map builder (one build at a time)
         self.fused_maps = True                # cvb200_sc_build_maps (one sync per scene); False: step-by-step coordinate manager
+        self.stem_gather4 = os.environ.get("CVB200_STEM_IM2COL", "0") != "1"   # False: stem as im2col + product (refresh() after changing)
         self.refresh()
 
     def upload(self, coords_host, feats_host):
@@ -136,15 +138,24 @@ class MinkUNetEngine:
     def refresh(self):
         """(Re)pack the model's parameters: call again after the weights changed."""
         m = self.model
-        self.w, self.im2col = {}, {}
+        self.w, self.im2col, self.gather4 = {}, {}, {}
 
         def put(name, conv, bn):
             w, b = _fold(conv, bn)
             cin = w.shape[1]
             if cin % 32 == 0:       # tensor-core op: [k3, cout, cin]
                 self.w[name] = (w.transpose(1, 2).contiguous(), b.contiguous() if b is not None else None, 0)
+            elif cin <= 4 and self.stem_gather4:
+                # small input width (the 3-channel 5^3 stem): the input is padded to 4 channels and the convolution kernel
+                # gathers 8 neighbours x 4 channels per k-block (CVB200_OP_CONV_TC_GATHER4): w4[co][4 k + c], K = 32 ceil(k3 / 8)
+                k3, cout = w.shape[0], w.shape[2]
+                kp = 32 * ((k3 + 7) // 8)
+                w4 = torch.zeros((kp // 4, 4, cout), dtype=w.dtype, device=w.device)
+                w4[:k3, :cin] = w
+                self.w[name] = (w4.reshape(1, kp, cout).transpose(1, 2).contiguous(), b.contiguous() if b is not None else None, 3)
+                self.gather4[name] = (k3, cin, kp)
             else:
-                # small input width (the 3-channel 5^3 stem): im2col + one [N, K^3*cin -> pad 32] x [., cout] tensor-core product
+                # small input width, fallback: im2col + one [N, K^3*cin -> pad 32] x [., cout] tensor-core product
                 k3, cout = w.shape[0], w.shape[2]
                 kp = (k3 * cin + 31) // 32 * 32
                 kp = (kp + cin - 1) // cin * cin if kp % cin else kp
@@ -244,7 +255,18 @@ class MinkUNetEngine:
         # stem: conv0 (5^3, stride 1) + bn0 + relu -> skip slot of level 1
         src = _Slice(feats.data_ptr(), feats.shape[0], feats.shape[1], 0, feats.shape[1])
         stem_table = cm.kernel_map(1, self.model.conv0p1s1.kernel_size)
-        if "conv0p1s1" in self.im2col:
+        if "conv0p1s1" in self.gather4:
+            k3, cin, kp = self.gather4["conv0p1s1"]
+            feats4 = torch.nn.functional.pad(feats, (0, 4 - cin)).contiguous()        # [N, 4]: one 16-byte vector per voxel
+            w, b, _ = self.w["conv0p1s1"]
+            o = _lib.ScOp()
+            o.kind, o.cin, o.cout, o.k3, o.ldi, o.ldo, o.ldr, o.relu = 3, kp, w.shape[1], k3, 4, skip[1].ld, 0, 1
+            o.n_out, o.n_in = n[1], feats4.shape[0]
+            o.w, o.bias, o.table = w.data_ptr(), b.data_ptr() if b is not None else None, stem_table.data_ptr()
+            src4 = _Slice(feats4.data_ptr(), feats4.shape[0], 4, 0, 4)
+            ops.append((o, src4, skip[1], None))
+            feats = feats4                     # kept alive with the program
+        elif "conv0p1s1" in self.im2col:
             k3, cin, kp = self.im2col["conv0p1s1"]
             col = arena.matrix(n[1], kp)
             o = _lib.ScOp()

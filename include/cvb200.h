@@ -230,6 +230,9 @@ int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t stem_ksize,
 #define CVB200_OP_CONV_TC 0
 #define CVB200_OP_CONV_SMALLCIN 1
 #define CVB200_OP_IM2COL 2        /* out[o, k*cin + c] = in[table[o,k], c] (0 if missing / padding), ldo % cin == 0 */
+#define CVB200_OP_CONV_TC_GATHER4 3 /* tcgen05 convolution of a 4-channel input (ldi = 4; the 3-channel stem padded with a zero
+                                   * channel): table [n_out, k3], w = [cout][K], K = cin = 32*ceil(k3/8), w[co][4*k + c]; the
+                                   * kernel gathers 8 neighbours x 4 channels per k-block, no im2col matrix */
 typedef struct cvb200_sc_op {
     int32_t kind, cin, cout, k3;
     int32_t ldi, ldo, ldr, relu;

@@ -215,6 +215,13 @@ def test_engine_matches_module_path_and_oracle():
     torch.testing.assert_close(xyz, wxyz, rtol=0, atol=0)
     torch.testing.assert_close(sc, wsc, rtol=1e-6, atol=0)
     torch.testing.assert_close(prob, wprob, rtol=1e-5, atol=1e-7)
+    # stem variants: 4-channel gather inside the convolution kernel (default) vs im2col + product
+    eng2 = MinkUNetEngine(model)
+    eng2.stem_gather4 = False
+    eng2.refresh()
+    alt = eng2(coords.cuda(), feats.cuda())
+    torch.cuda.synchronize()
+    assert float((alt - got).abs().max()) <= 2e-3 * scale
     # second call on another scene re-uses the packed weights
     coords2, feats2 = _scene(n=1000, G=30, batch=1, cin=3, seed=12)
     out2 = eng(coords2.cuda(), feats2.cuda())
