@@ -251,6 +251,8 @@ def main():
         _lib.load().cvb200_sc_set_conv_options(o[0], o[1])
         if len(o) > 2:
             _lib.load().cvb200_sc_set_conv_impl(o[2])
+        if len(o) > 3:
+            _lib.load().cvb200_sc_set_conv_debug(o[3])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

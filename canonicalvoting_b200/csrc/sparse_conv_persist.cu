@@ -126,7 +126,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
-            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), 2);      // both MMA warps
+            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), (P.dbg & 0x40000) ? 1 : 2);      // both MMA warps
             tm_mbar_init(tm_smem_u32(&H.acc_empty[b]), 4);
             tm_mbar_init(tm_smem_u32(&H.turn[b]), 1);
         }
@@ -185,18 +185,19 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // order, stages are released in order, and the first k-block of a unit overwrites the accumulator before anything
         // is added to it.  Both warps commit to acc_full (count 2).
         const int me = warp == 4 ? 0 : 1;
+        const int issuers = (P.dbg & 0x40000) ? 1 : 2;            // measurement aid: one issuer only (warp 12 idles)
         int li = 0, n_base = 0;
-        for (int u = blockIdx.x; u < P.n_units; u += gridDim.x, li++) {
+        for (int u = blockIdx.x; u < P.n_units && me < issuers; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.nc >> 3) << 17) | ((uint32_t)(kPsM >> 4) << 24);
             const int buf = li & 1;
-            const int first = U.kb0 + ((me - n_base) & 1);        // my first k-block of this unit
+            const int first = issuers == 1 ? U.kb0 : U.kb0 + ((me - n_base) & 1);        // my first k-block of this unit
             const uint32_t d_tmem = tmem + (uint32_t)(buf * P.acc_stride);
             if (first == U.kb0 && first < U.kb1) {
                 tm_mbar_wait(tm_smem_u32(&H.acc_empty[buf]), (uint32_t)(((li >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            for (int it = first; it < U.kb1; it += 2) {
+            for (int it = first; it < U.kb1; it += issuers) {
                 const int n = n_base + it - U.kb0;
                 const int round = n / P.stages, s = n - round * P.stages;
                 const long long t0 = tr ? clock64() : 0;
@@ -206,7 +207,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
                 if (!(P.dbg & 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
                 // my turn: the other warp has issued k-block n - 1
-                if (n > 0) tm_mbar_wait(tm_smem_u32(&H.turn[me]), (uint32_t)(((n >> 1) + me + 1) & 1));
+                if (n > 0 && issuers == 2) tm_mbar_wait(tm_smem_u32(&H.turn[me]), (uint32_t)(((n >> 1) + me + 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tm_elect_one()) {
                     if (!(P.dbg & 4)) {
