@@ -10,18 +10,20 @@
 //   * ONE CTA per SM walks a list of work units.  A unit = (row tile of 128 outputs, channel split, piece of the
 //     k-block sequence); the host plans whole tiles for the full waves and cuts the tiles of the last, partial wave
 //     (or all tiles of a small level) into `ks` pieces so that every SM gets the same amount of k-blocks.
-//   * roles: warp 0 = weight-tile TMA producer, warps 1 and 12 = MMA issuers (alternating k-blocks; warp 1 owns the TMEM
-//     allocation), warps 2-7 = gather
-//     producers (16-byte cp.async straight from the feature matrix into the 128B-swizzled A tile, zero-length copy =
-//     zero fill for a missing neighbour; neighbour ids are read from the table one offset ahead, no staging pass),
-//     warps 8-11 = epilogue.  full/empty mbarriers per ring stage (up to 8 stages, ~200 KB of shared memory).
+//   * roles (13 warps): warp 0 = weight-tile TMA producer; warps 4 and 12 = MMA issuers, alternating k-blocks under a
+//     strict issue order (warp 4 owns the TMEM allocation); warps 1,2,3,5 = gather producers, each filling whole k-blocks
+//     alone (16-byte cp.async straight from the feature matrix into the 128B-swizzled A tile, zero-length copy = zero
+//     fill for a missing neighbour; neighbour ids are read from the table one k-block ahead and passed by shuffles, no
+//     staging pass); warps 8-11 = epilogue; warps 6,7 idle (spare producers).  Issuers and TMA share one warp scheduler
+//     (warp % 4 == 0) that hosts no producer.  full/empty mbarriers per ring stage (7-8 stages, ~213 KB of shared memory).
 //   * TWO accumulators in tensor memory: the epilogue of unit i (tcgen05.ld -> bias/residual/ReLU -> global) runs
-//     while the MMA warp already accumulates unit i+1.
+//     (through a swizzled staging tile: coalesced 128-byte row stores) while the MMA warps already accumulate unit i+1.
 //   * pieces of a split tile add their partial sums into a zero-initialised, self-cleaning scratch tile
 //     (red.global.add.v4.f32, coalesced [4-column group][row] layout); the piece that arrives last (per-tile counter)
 //     reads the sum back, re-zeroes the scratch and applies the epilogue -- no memset, no finishing launch.
-//   * programmatic dependent launch: barrier init and the TMEM allocation of convolution i+1 overlap the tail of
-//     convolution i (griddepcontrol.wait before the first global read).
+//   * programmatic dependent launch: barrier init, TMEM allocation, the first weight tiles and neighbour ids of
+//     convolution i+1 overlap the tail of convolution i (griddepcontrol.wait only in the gather and epilogue roles).
+//   * a 4-channel input (the padded 3-channel 5^3 stem) is gathered 8 neighbours per k-block (g4 mode): no im2col.
 #include <cuda.h>
 
 #include <map>
