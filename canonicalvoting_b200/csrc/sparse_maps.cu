@@ -106,15 +106,27 @@ __global__ void mp_link_children_kernel(const int4 *__restrict__ coords, const i
     }
 }
 
+// Stride-1 kernel map of a level onto itself.  The map is symmetric -- if j is the neighbour of o at offset k, o is the
+// neighbour of j at the mirrored offset K^3-1-k -- so only the lower half of the offsets is looked up in the hash map and
+// the mirrored entry is written alongside (the table is pre-filled with -1, the centre offset is the voxel itself):
+// half the hash probes of the 5^3 stem map (6.25 M for a 50k-voxel scene) and of the 3^3 maps.
 __global__ void mp_kernel_map_kernel(const int4 *__restrict__ coords, const int *__restrict__ cnt, const unsigned long long *__restrict__ keys,
                                      const int *__restrict__ vals, unsigned int mask, int ksize, int step, int *__restrict__ nbr) {
-    const int k3 = ksize * ksize * ksize, h = ksize / 2;
-    const long long total = (long long)(*cnt) * k3;
+    const int k3 = ksize * ksize * ksize, h = ksize / 2, mid = k3 / 2;
+    const long long total = (long long)(*cnt) * (mid + 1);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int o = (int)(t / k3), k = (int)(t - (long long)o * k3);
+        const int o = (int)(t / (mid + 1)), k = (int)(t - (long long)o * (mid + 1));
+        if (k == mid) {
+            nbr[(size_t)o * k3 + mid] = o;
+            continue;
+        }
         const int ix = k % ksize, iy = (k / ksize) % ksize, iz = k / (ksize * ksize);
         const int4 c = __ldg(coords + o);
-        nbr[t] = hash_lookup(keys, vals, mask, pack_coord(c.x, c.y + (ix - h) * step, c.z + (iy - h) * step, c.w + (iz - h) * step));
+        const int j = hash_lookup(keys, vals, mask, pack_coord(c.x, c.y + (ix - h) * step, c.z + (iy - h) * step, c.w + (iz - h) * step));
+        if (j >= 0) {
+            nbr[(size_t)o * k3 + k] = j;
+            nbr[(size_t)j * k3 + (k3 - 1 - k)] = o;
+        }
     }
 }
 
@@ -175,6 +187,8 @@ extern "C" int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t 
     mp_arange_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>((int *)(ws + L->arange), n_ub);
     CVB_CUDA(cudaMemsetAsync(keys(0), 0xff, 8 * (size_t)L->capacity, stream));
     mp_insert_rows_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(0), counts, keys(0), vals(0), mask);
+    if (stem_ksize) CVB_CUDA(cudaMemsetAsync(ws + L->stem_table, 0xff, 4 * (size_t)n_ub * stem_ksize * stem_ksize * stem_ksize, stream));
+    for (int l = 0; l <= n_down; l++) CVB_CUDA(cudaMemsetAsync(ws + L->nbr3[l], 0xff, 4 * (size_t)n_ub * 27, stream));
     if (stem_ksize)
         mp_kernel_map_kernel<<<8 * kMapBlocks, kMapThreads, 0, stream>>>(coords(0), counts, keys(0), vals(0), mask, stem_ksize, 1,
                                                                         (int *)(ws + L->stem_table));
