@@ -82,6 +82,7 @@ class MapsLayout(ctypes.Structure):
 
 
 SIGNATURES.update({
+    "cvb200_sc_quantize": (ctypes.c_int, [_f, _i64, ctypes.c_float, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "cvb200_sc_maps_layout": (ctypes.c_int, [_i64, _i32, _i32, ctypes.POINTER(MapsLayout)]),
     "cvb200_sc_build_maps": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, ctypes.POINTER(MapsLayout), _vp, _vp]),
 })

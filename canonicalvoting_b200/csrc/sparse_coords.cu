@@ -176,3 +176,54 @@ extern "C" int cvb200_sc_kernel_map(const int32_t *d_out_coords, int64_t n_out, 
     CVB_LAUNCH_CHECK("sc_kernel_map_kernel");
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// On-device voxelisation: ME.utils.sparse_quantize (utils/dataloader.py:197, sunrgbd/brnetcanon.py:218) -- the step right
+// before the hot path.  voxel = floor(p / quantization_size) in float32 (numpy's arithmetic for a float32 array), one
+// representative point per occupied voxel: the FIRST in input order (atomicMin of the row index per voxel key), so the
+// result is deterministic and equal to the host implementation in canonicalvoting_b200/sparse/utils.py.
+namespace cvb200 {
+
+__global__ void sc_quantize_insert_kernel(const float *__restrict__ xyz, int n, float qsize, int batch, int4 *__restrict__ voxel,
+                                          unsigned long long *keys, int *vals, unsigned int mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = __ldg(xyz + 3 * (size_t)i), y = __ldg(xyz + 3 * (size_t)i + 1), z = __ldg(xyz + 3 * (size_t)i + 2);
+    if (qsize > 0.f) { x = __fdiv_rn(x, qsize); y = __fdiv_rn(y, qsize); z = __fdiv_rn(z, qsize); }
+    const int4 v = make_int4(batch, (int)floorf(x), (int)floorf(y), (int)floorf(z));
+    voxel[i] = v;
+    atomicMin(vals + hash_insert(keys, mask, pack_coord(v.x, v.y, v.z, v.w)), i);   // vals pre-filled with INT_MAX
+}
+
+// rep[i] = first point of i's voxel, flag[i] = 1 iff i is that point
+__global__ void sc_quantize_lookup_kernel(const int4 *__restrict__ voxel, int n, const unsigned long long *__restrict__ keys,
+                                          const int *__restrict__ vals, unsigned int mask, int *__restrict__ rep, int *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 v = voxel[i];
+    const int r = hash_lookup(keys, vals, mask, pack_coord(v.x, v.y, v.z, v.w));
+    rep[i] = r;
+    flag[i] = r == i;
+}
+
+}  // namespace cvb200
+
+extern "C" int cvb200_sc_quantize(const float *d_xyz, int64_t n, float quantization_size, int32_t batch, void *d_keys, int32_t *d_vals,
+                                  int64_t capacity, int32_t *d_voxel, int32_t *d_rep, int32_t *d_flag, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVB_REQUIRE(n >= 0 && n < (1LL << 31) && pow2(capacity) && capacity >= 2 * n && batch >= 0 && batch < 65536, CVB200_EINVAL,
+                "sc_quantize: bad sizes (n=%lld, capacity=%lld, batch=%d)", (long long)n, (long long)capacity, batch);
+    CVB_REQUIRE(d_keys && d_vals, CVB200_EINVAL, "sc_quantize: NULL table");
+    CVB_CUDA(cudaMemsetAsync(d_keys, 0xff, sizeof(unsigned long long) * (size_t)capacity, stream));
+    CVB_CUDA(cudaMemsetAsync(d_vals, 0x7f, sizeof(int) * (size_t)capacity, stream));
+    if (n == 0) return 0;
+    CVB_REQUIRE(d_xyz && d_voxel && d_rep && d_flag, CVB200_EINVAL, "sc_quantize: NULL argument");
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    const unsigned int mask = (unsigned int)(capacity - 1);
+    sc_quantize_insert_kernel<<<blocks, 256, 0, stream>>>(d_xyz, (int)n, quantization_size, batch, (int4 *)d_voxel,
+                                                         (unsigned long long *)d_keys, d_vals, mask);
+    sc_quantize_lookup_kernel<<<blocks, 256, 0, stream>>>((const int4 *)d_voxel, (int)n, (const unsigned long long *)d_keys, d_vals, mask,
+                                                         d_rep, d_flag);
+    CVB_LAUNCH_CHECK("sc_quantize");
+    return 0;
+}

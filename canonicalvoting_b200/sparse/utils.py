@@ -1,6 +1,8 @@
 """ME.utils subset used by the reference: batched_coordinates (train_joint.py:82, eval_joint.py:64),
-sparse_quantize (utils/dataloader.py:197) and kaiming_normal_ (utils/resnet.py:112).  Host-side helpers
-of the data loader; semantics from recollection of MinkowskiEngine 0.5.x [ME-recall]."""
+sparse_quantize (utils/dataloader.py:197; device='cuda' form at sunrgbd/brnetcanon.py:218) and kaiming_normal_
+(utils/resnet.py:112).  Semantics from recollection of MinkowskiEngine 0.5.x [ME-recall].  CPU inputs are handled on the
+host with numpy (the data loader's workers); CUDA float32 inputs (or device='cuda') are voxelised on the device by
+cvb200_sc_quantize -- same result: the first point of every voxel, in input order."""
 import math
 
 import numpy as np
@@ -15,7 +17,7 @@ def batched_coordinates(coords, dtype=torch.int32, device=None):
         if c.is_floating_point():
             c = torch.floor(c)
         c = c.to(torch.int64)
-        out.append(torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int64), c], 1))
+        out.append(torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int64, device=c.device), c], 1))
     res = torch.cat(out, 0).to(dtype) if out else torch.zeros((0, 4), dtype=dtype)
     return res.to(device) if device is not None else res
 
@@ -25,9 +27,15 @@ def sparse_quantize(coordinates, features=None, labels=None, quantization_size=N
     """floor(coordinates / quantization_size), one representative row per occupied voxel (the first in input
     order; ME leaves the choice unspecified).  Returns what ME returns for the argument combination used by the
     reference: (unique_coords[, features][, labels][, index][, inverse])."""
+    want_cuda = device is not None and torch.device(device).type == "cuda"
+    if isinstance(coordinates, torch.Tensor) and (coordinates.is_cuda or want_cuda) and coordinates.dtype == torch.float32:
+        return _sparse_quantize_cuda(coordinates.to(device) if want_cuda and not coordinates.is_cuda else coordinates, features, labels,
+                                     quantization_size, return_index, return_inverse)
     c = np.asarray(coordinates.cpu() if isinstance(coordinates, torch.Tensor) else coordinates)
     if quantization_size is not None:
         c = np.floor(c / quantization_size)
+    elif np.issubdtype(c.dtype, np.floating):
+        c = np.floor(c)                          # like batched_coordinates: float inputs are floored, not truncated [ME-recall]
     c = c.astype(np.int64)
     _, index, inverse = np.unique(c, axis=0, return_index=True, return_inverse=True)
     order = np.sort(index)                      # keep input order among the representatives
@@ -42,6 +50,39 @@ def sparse_quantize(coordinates, features=None, labels=None, quantization_size=N
         outs.append(torch.from_numpy(order))
     if return_inverse:
         outs.append(torch.from_numpy(remap[inverse.reshape(-1)]))
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def _sparse_quantize_cuda(xyz, features, labels, quantization_size, return_index, return_inverse):
+    """Device path of sparse_quantize: one hash-map pass (first point per voxel by atomicMin of the row index) + a scan."""
+    import ctypes
+
+    from .. import _lib
+    from .coords import _ptr, _stream
+    L = _lib.load()
+    xyz = xyz.contiguous()
+    n, dev = xyz.shape[0], xyz.device
+    cap = int(L.cvb200_sc_hash_capacity(n))
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    vals = torch.empty(cap, dtype=torch.int32, device=dev)
+    voxel = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    rep = torch.empty(n, dtype=torch.int32, device=dev)
+    flag = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.cvb200_sc_quantize(_ptr(xyz), n, ctypes.c_float(float(quantization_size) if quantization_size is not None else 0.0), 0,
+                                  _ptr(keys), _ptr(vals), cap, _ptr(voxel), _ptr(rep), _ptr(flag), _stream())
+        _lib.check(rc, "cvb200_sc_quantize")
+    index = torch.nonzero(flag, as_tuple=False).view(-1)            # ascending = input order (one host sync: the voxel count)
+    outs = [voxel[index, 1:].contiguous()]
+    if features is not None:
+        outs.append(features[index.to(features.device)] if isinstance(features, torch.Tensor) else features[index.cpu().numpy()])
+    if labels is not None:
+        outs.append(labels[index.to(labels.device)] if isinstance(labels, torch.Tensor) else labels[index.cpu().numpy()])
+    if return_index:
+        outs.append(index)
+    if return_inverse:
+        excl = torch.cumsum(flag, 0) - flag
+        outs.append(excl[rep.long()].long())
     return outs[0] if len(outs) == 1 else tuple(outs)
 
 

@@ -202,6 +202,14 @@ int cvb200_sc_set_conv_debug(int32_t mask);
  * first 256 k-blocks of CTA 0 for the MMA thread, one gather warp and the weight-TMA thread; NULL switches it off. */
 int cvb200_sc_set_conv_trace(void *d_trace);
 
+/* On-device voxelisation = ME.utils.sparse_quantize (utils/dataloader.py:197, sunrgbd/brnetcanon.py:218): d_xyz float32 [n,3];
+ * voxel = floor(p / quantization_size) evaluated in float32 (quantization_size <= 0: floor(p)); d_voxel int32 [n,4] receives
+ * (batch, x, y, z) of every point; d_rep[i] = row of the FIRST point of i's voxel, d_flag[i] = 1 iff i is that point.  The
+ * caller compacts (indices = positions of the flags, inverse = exclusive_scan(flag)[rep]).  d_keys (uint64) / d_vals (int32):
+ * scratch hash map of `capacity` = cvb200_sc_hash_capacity(n) entries. */
+int cvb200_sc_quantize(const float *d_xyz, int64_t n, float quantization_size, int32_t batch, void *d_keys, int32_t *d_vals,
+                       int64_t capacity, int32_t *d_voxel, int32_t *d_rep, int32_t *d_flag, void *stream);
+
 /* All coordinate levels and kernel maps of a MinkUNet-shaped network in one enqueue, without the host in the loop
  * (csrc/sparse_maps.cu).  Level l has tensor stride 2^l; every table is allocated for the upper bound n inside ONE workspace
  * of layout->total_bytes bytes (offsets below are in bytes); the real sizes are written to counts[0 .. n_down] on the

@@ -375,3 +375,22 @@ def test_edge_cases_tiny_inputs():
     model = MinkUNet34C(3, 64).cuda().eval()
     out = MinkUNetEngine(model)(coords, torch.rand(10, 3).cuda())
     assert out.shape == (10, 64) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("qsize", [0.03, None])
+def test_sparse_quantize_on_device_equals_host(qsize):
+    """ME.utils.sparse_quantize (utils/dataloader.py:197): the device path (hash map, first point per voxel) returns exactly
+    what the numpy path returns: voxel coordinates in first-occurrence order, representative indices, inverse map."""
+    import MinkowskiEngine as ME
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(20000, 3, generator=g) * (3.0 if qsize else 40.0) - (1.0 if qsize else 10.0)).float()   # negatives included
+    feats = torch.rand(20000, 3, generator=g)
+    hc, hf, hi, hv = ME.utils.sparse_quantize(pts, features=feats, quantization_size=qsize, return_index=True, return_inverse=True)
+    dc, df, di, dv = ME.utils.sparse_quantize(pts.cuda(), features=feats.cuda(), quantization_size=qsize, return_index=True, return_inverse=True)
+    assert 0 < len(hc) < 20000
+    assert torch.equal(dc.cpu(), hc) and torch.equal(di.cpu(), hi) and torch.equal(dv.cpu(), hv)
+    assert torch.equal(df.cpu(), hf)
+    only_index = ME.utils.sparse_quantize(pts.cuda(), quantization_size=qsize, return_index=True)[1]
+    assert torch.equal(only_index.cpu(), hi)
+    bc = ME.utils.batched_coordinates([dc, dc[:10]])
+    assert bc.is_cuda and bc.shape == (len(dc) + 10, 4) and int(bc[-1, 0]) == 1
