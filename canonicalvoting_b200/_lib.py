@@ -49,6 +49,11 @@ SIGNATURES.update({
 })
 
 SIGNATURES.update({
+    "cvb200_obb_nms": (ctypes.c_int, [_f, _f, _vp, _i32, _i32, ctypes.c_double, _vp, _vp, _vp]),
+    "cvb200_obb_iou_matrix": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _vp]),
+})
+
+SIGNATURES.update({
     "cvb200_sc_hash_capacity": (_i64, [_i64]),
     "cvb200_sc_build_table": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "cvb200_sc_down_flags": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),

@@ -50,3 +50,7 @@ class HoughVoting(torch.nn.Module):
 
     def forward(self, points, xyz, scale, obj):
         return HVFunction.apply(points, xyz, scale, obj, self.res, self.num_rots)
+
+
+# the detection post-process that follows back_project in the eval scripts (eval_joint.py:265-280)
+from .obb import get_iou_obb, iou_matrix, nms_per_class  # noqa: E402,F401

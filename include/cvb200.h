@@ -134,6 +134,16 @@ int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, const float 
                         const cvb200_bp_params *params, float *d_boxes, float *d_scores, int32_t *d_classes,
                         int32_t *d_counts, int32_t *d_trace, void *d_work, size_t work_bytes, void *stream);
 
+/* Detection post-process after the candidate loop (eval_joint.py:265-280): per-class greedy NMS of oriented boxes with
+ * get_iou_obb (utils/calc_map.py:6-21: xz-rectangle intersection x y-overlap), float64 geometry.  d_boxes [k,8,3]
+ * (corners 0-3 top face, 4-7 bottom face), d_scores [k], d_classes int32 [k] (classes outside [0,nclasses) are dropped).
+ * d_pick receives the kept indices class by class in pick order (score descending; ties: larger index first, i.e. a
+ * stable argsort + "take the last" as nms() at eval_joint.py:75-89 does), *d_n_pick their number.  k <= 2048. */
+int cvb200_obb_nms(const float *d_boxes, const float *d_scores, const int32_t *d_classes, int32_t k, int32_t nclasses,
+                   double overlap_threshold, int32_t *d_pick, int32_t *d_n_pick, void *stream);
+/* out[i*nb + j] = get_iou_obb(a[i], b[j]) as float64 (utils/calc_map.py:6-21; used by the mAP evaluation, :78-168). */
+int cvb200_obb_iou_matrix(const float *d_a, int32_t na, const float *d_b, int32_t nb, double *d_out, void *stream);
+
 /* ------------------------------------------------- sparse-voxel U-Net: coordinates + convolution ---- */
 /* These replace what the reference gets from the external MinkowskiEngine package (v0.5.3, README.md:53):
  * ME.SparseTensor's coordinate manager (train_joint.py:250, eval_joint.py:169) and the kernels behind
