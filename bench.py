@@ -354,8 +354,7 @@ def main():
 
     def step_scene(eng, j, maps=None):
         c_d, f_d, cr, dm = dev_scenes[j % n_rot]
-        xyz, scale, cls, prob = eng.predict(c_d, f_d, maps)
-        points = (c_d[:, 1:].float() * res).contiguous()              # eval_joint.py:193
+        xyz, scale, cls, prob, points = eng.predict(c_d, f_d, maps, res=res)   # points = coords * res (eval_joint.py:193), same kernel
         return H.forward_host(points, xyz, scale, prob, res, R, cr, dm)
 
     def run_steps(lane, eng, j0, k):
@@ -405,8 +404,8 @@ def main():
     def step_e2e(eng, fut):
         # fut: upload (pinned host -> device) + coordinate maps of THIS scene, started while the previous scene ran
         c, f, _, _ = fut.result()
-        xyz, scale, cls, prob = eng.predict(None, None, fut)
-        go, gr, gs = hv_cuda.forward((c[:, 1:].float() * res).contiguous(), xyz, scale, prob, res_t, rots_t)
+        xyz, scale, cls, prob, points = eng.predict(None, None, fut, res=res)
+        go, gr, gs = hv_cuda.forward(points, xyz, scale, prob, res_t, rots_t)
         peak = torch.stack([go.max(), go.argmax().float()])
         return peak.cpu()          # D2H read of the step's result (peak value + voxel)
 

@@ -95,6 +95,7 @@ SIGNATURES.update({
 SIGNATURES.update({
     "cvb200_sc_run_program": (ctypes.c_int, [ctypes.POINTER(ScOp), _i32, _vp]),
     "cvb200_head_decode": (ctypes.c_int, [_f, _i32, _i64, _i32, _i32, _f, _f, _vp, _f, _vp]),
+    "cvb200_head_decode_points": (ctypes.c_int, [_f, _i32, _i64, _i32, _i32, _f, _f, _vp, _f, _vp, ctypes.c_float, _f, _vp]),
 })
 
 _lib = None

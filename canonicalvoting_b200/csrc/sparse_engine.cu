@@ -76,11 +76,19 @@ __global__ void sc_im2col_kernel(const float *__restrict__ in, int ldi, int cin,
 
 // Head decode of the joint model (eval_joint.py:173-190): one thread per point.
 //   feats [n, 6*C + C + 1]: xyz[C][3] | scale[C][3] | class logits [C+1] (last = background)
+// With `coords` (int32 rows (batch, x, y, z)) it also writes the vote op's first argument, points = coords[:, 1:] * res
+// (eval_joint.py:193), so that no torch kernel sits between the network and hv_cuda.forward.
 __global__ void head_decode_kernel(const float *__restrict__ f, int ld, int n, int nclasses, int log_scale,
                                    float *__restrict__ xyz, float *__restrict__ scale, long long *__restrict__ cls,
-                                   float *__restrict__ prob) {
+                                   float *__restrict__ prob, const int4 *__restrict__ coords, float res, float *__restrict__ points) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (coords) {
+        const int4 c = __ldg(coords + i);
+        points[3 * (size_t)i] = __fmul_rn((float)c.y, res);
+        points[3 * (size_t)i + 1] = __fmul_rn((float)c.z, res);
+        points[3 * (size_t)i + 2] = __fmul_rn((float)c.w, res);
+    }
     const float *row = f + (size_t)i * ld;
     const float *logit = row + 6 * nclasses;
     float best = -INFINITY, best_obj = -INFINITY;
@@ -153,6 +161,21 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
     return 0;
 }
 
+extern "C" int cvb200_head_decode_points(const float *d_feats, int32_t ld, int64_t n, int32_t nclasses, int32_t log_scale, float *d_xyz,
+                                         float *d_scale, int64_t *d_class, float *d_prob, const int32_t *d_coords, float res,
+                                         float *d_points, void *stream_) {
+    CVB_REQUIRE(n >= 0 && n < (1LL << 31) && nclasses >= 1 && nclasses <= 64 && ld >= 7 * nclasses + 1, CVB200_EINVAL,
+                "head_decode: bad sizes (n=%lld, nclasses=%d, ld=%d)", (long long)n, nclasses, ld);
+    if (n == 0) return 0;
+    CVB_REQUIRE(d_feats && d_xyz && d_scale && d_class && d_prob && (d_coords == nullptr) == (d_points == nullptr), CVB200_EINVAL,
+                "head_decode: NULL argument (coords and points go together)");
+    head_decode_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream_>>>(d_feats, ld, (int)n, nclasses, log_scale, d_xyz,
+                                                                                     d_scale, (long long *)d_class, d_prob,
+                                                                                     (const int4 *)d_coords, res, d_points);
+    CVB_LAUNCH_CHECK("head_decode_kernel");
+    return 0;
+}
+
 extern "C" int cvb200_head_decode(const float *d_feats, int32_t ld, int64_t n, int32_t nclasses, int32_t log_scale, float *d_xyz,
                                   float *d_scale, int64_t *d_class, float *d_prob, void *stream_) {
     CVB_REQUIRE(n >= 0 && n < (1LL << 31) && nclasses >= 1 && nclasses <= 64 && ld >= 7 * nclasses + 1, CVB200_EINVAL,
@@ -160,7 +183,7 @@ extern "C" int cvb200_head_decode(const float *d_feats, int32_t ld, int64_t n, i
     if (n == 0) return 0;
     CVB_REQUIRE(d_feats && d_xyz && d_scale && d_class && d_prob, CVB200_EINVAL, "head_decode: NULL argument");
     head_decode_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream_>>>(d_feats, ld, (int)n, nclasses, log_scale, d_xyz,
-                                                                                     d_scale, (long long *)d_class, d_prob);
+                                                                                     d_scale, (long long *)d_class, d_prob, nullptr, 0.f, nullptr);
     CVB_LAUNCH_CHECK("head_decode_kernel");
     return 0;
 }

@@ -334,8 +334,10 @@ class MinkUNetEngine:
                 del old_keep
         return out
 
-    def decode(self, feats):
-        """Head decode (eval_joint.py:173-190): features [N, 7*C+1] -> (xyz_pred, scale_pred, class_pred int64, prob_pred)."""
+    def decode(self, feats, coords=None, res=None):
+        """Head decode (eval_joint.py:173-190): features [N, 7*C+1] -> (xyz_pred, scale_pred, class_pred int64, prob_pred).
+        With `coords` (int32 [N,4]) and `res` the same kernel also returns scan_points = coords[:, 1:] * res (eval_joint.py:193)
+        as a fifth tensor: the first argument of hv_cuda.forward."""
         L = _lib.load()
         n = feats.shape[0]
         xyz = torch.empty((n, 3), dtype=torch.float32, device=feats.device)
@@ -343,10 +345,23 @@ class MinkUNetEngine:
         cls = torch.empty((n,), dtype=torch.int64, device=feats.device)
         prob = torch.empty((n,), dtype=torch.float32, device=feats.device)
         with torch.cuda.device(feats.device):
+            if coords is not None:
+                coords = coords.to(torch.int32).contiguous()
+                points = torch.empty((n, 3), dtype=torch.float32, device=feats.device)
+                rc = L.cvb200_head_decode_points(_ptr(feats), feats.stride(0), n, self.nclasses, 1 if self.log_scale else 0, _ptr(xyz),
+                                                 _ptr(scale), _ptr(cls), _ptr(prob), _ptr(coords), ctypes.c_float(float(res)), _ptr(points),
+                                                 _stream())
+                _lib.check(rc, "cvb200_head_decode_points")
+                return xyz, scale, cls, prob, points
             rc = L.cvb200_head_decode(_ptr(feats), feats.stride(0), n, self.nclasses, 1 if self.log_scale else 0, _ptr(xyz),
                                       _ptr(scale), _ptr(cls), _ptr(prob), _stream())
             _lib.check(rc, "cvb200_head_decode")
         return xyz, scale, cls, prob
 
-    def predict(self, coords, feats, maps=None):
-        return self.decode(self(coords, feats, maps))
+    def predict(self, coords, feats, maps=None, res=None):
+        """Network + head decode.  With `res` the tuple has a fifth element: scan_points = coords[:, 1:] * res."""
+        if res is None:
+            return self.decode(self(coords, feats, maps))
+        if maps is not None:
+            coords = maps.result()[0]
+        return self.decode(self(coords, feats, maps), coords, res)

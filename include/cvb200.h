@@ -271,6 +271,11 @@ int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, void *stream);
  * config/config.yaml:17), class_pred [n] int64 (argmax over the C object classes), prob_pred [n]. */
 int cvb200_head_decode(const float *d_feats, int32_t ld, int64_t n, int32_t nclasses, int32_t log_scale, float *d_xyz,
                        float *d_scale, int64_t *d_class, float *d_prob, void *stream);
+/* Same, plus the vote op's first argument in the same pass: d_points [n,3] = d_coords[:, 1:4] * res for int32 coordinate rows
+ * (batch, x, y, z) (eval_joint.py:193: `scan_points = coords * res`). */
+int cvb200_head_decode_points(const float *d_feats, int32_t ld, int64_t n, int32_t nclasses, int32_t log_scale, float *d_xyz,
+                              float *d_scale, int64_t *d_class, float *d_prob, const int32_t *d_coords, float res, float *d_points,
+                              void *stream);
 
 /* dW[k] [ca,cb] = sum_r A[ia(r,k),:]^T (x) B[ib(r,k),:] over the table rows r;
  * table_on_b = 0: ia = table[r,k], ib = r;  table_on_b = 1: ia = r, ib = table[r,k].  d_dw is overwritten. */

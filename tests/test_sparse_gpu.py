@@ -215,6 +215,10 @@ def test_engine_matches_module_path_and_oracle():
     torch.testing.assert_close(xyz, wxyz, rtol=0, atol=0)
     torch.testing.assert_close(sc, wsc, rtol=1e-6, atol=0)
     torch.testing.assert_close(prob, wprob, rtol=1e-5, atol=1e-7)
+    # decode + scan_points in one kernel: points == coords[:, 1:] * res exactly (eval_joint.py:193)
+    out5 = eng.decode(got, coords.cuda(), 0.03)
+    assert torch.equal(out5[0], xyz) and torch.equal(out5[3], prob)
+    assert torch.equal(out5[4], coords.cuda()[:, 1:].float() * 0.03)
     # stem variants: 4-channel gather inside the convolution kernel (default) vs im2col + product
     eng2 = MinkUNetEngine(model)
     eng2.stem_gather4 = False
