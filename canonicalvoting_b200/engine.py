@@ -143,6 +143,10 @@ class MinkUNetEngine:
         def put(name, conv, bn):
             w, b = _fold(conv, bn)
             cin = w.shape[1]
+            if w.shape[2] % 16:      # the tensor-core kernel needs cout % 16 == 0 (the 8-channel heads of the per-category models,
+                pad = 16 - w.shape[2] % 16          # eval_separate.py:138): zero output channels, cut off again by build()
+                w = torch.nn.functional.pad(w, (0, pad))
+                b = torch.nn.functional.pad(b, (0, pad)) if b is not None else None
             if cin % 32 == 0:       # tensor-core op: [k3, cout, cin]
                 self.w[name] = (w.transpose(1, 2).contiguous(), b.contiguous() if b is not None else None, 0)
             elif cin <= 4 and self.stem_gather4:
@@ -290,7 +294,7 @@ class MinkUNetEngine:
             self._op(ops, conv, x, up, d["up_table"], relu=True)
             ts = fine
             x = self._blocks(ops, arena, block, cm, ts, cat[fine])
-        out = arena.matrix(n[1], self.out_channels)
+        out = arena.matrix(n[1], self.w["final"][0].shape[1])          # padded to a multiple of 16 channels
         self._op(ops, "final", x, out, self._identity(cm, 1), relu=False)
         buf = arena.commit()
         arr = (_lib.ScOp * len(ops))()
@@ -298,7 +302,7 @@ class MinkUNetEngine:
             o.in_, o.out = src_.ptr, dst_.ptr
             o.residual = res_.ptr if res_ is not None else None
             arr[i] = o
-        return arr, arena.tensor(out), [cm, feats, buf]
+        return arr, arena.tensor(out)[:, :self.out_channels], [cm, feats, buf]
 
     # ------------------------------------------------------------------ execution
     def __call__(self, coords, feats, maps=None):
@@ -357,6 +361,17 @@ class MinkUNetEngine:
                                       _ptr(scale), _ptr(cls), _ptr(prob), _stream())
             _lib.check(rc, "cvb200_head_decode")
         return xyz, scale, cls, prob
+
+    def decode_separate(self, feats):
+        """Head decode of a per-category model (eval_separate.py:169-182): 8 channels = xyz[3] | scale[3] | objectness logits[2]
+        -> (xyz_pred, scale_pred (exp() if log_scale), prob_pred = softmax(logits)[:, 1]).  Several per-category engines can
+        share ONE coordinate-map handle of a scene (`maps=` of prefetch()), which is what makes the 9-models-per-scene eval cheap."""
+        if feats.shape[1] != 8:
+            raise RuntimeError("decode_separate: 8 output channels expected (xyz 3, scale 3, objectness 2)")
+        xyz = feats[:, :3].contiguous()
+        scale = torch.exp(feats[:, 3:6]) if self.log_scale else feats[:, 3:6].contiguous()
+        prob = torch.softmax(feats[:, 6:8], dim=-1)[:, 1].contiguous()
+        return xyz, scale.contiguous(), prob
 
     def predict(self, coords, feats, maps=None, res=None):
         """Network + head decode.  With `res` the tuple has a fifth element: scan_points = coords[:, 1:] * res."""

@@ -398,3 +398,27 @@ def test_sparse_quantize_on_device_equals_host(qsize):
     assert torch.equal(only_index.cpu(), hi)
     bc = ME.utils.batched_coordinates([dc, dc[:10]])
     assert bc.is_cuda and bc.shape == (len(dc) + 10, 4) and int(bc[-1, 0]) == 1
+
+
+def test_per_category_engines_share_one_coordinate_map():
+    """eval_separate.py:136-186 runs 9 per-category MinkUNet34C(3, 8) models on the same scene: the engines share one
+    prefetch() handle (maps built once) and decode_separate gives the script's xyz / scale / objectness."""
+    from canonicalvoting_b200.engine import MinkUNetEngine
+    from canonicalvoting_b200.minkunet import MinkUNet34C
+    coords, feats = _scene(n=3000, G=40, batch=1, cin=3, seed=31)
+    engines = []
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        engines.append(MinkUNetEngine(MinkUNet34C(3, 8).cuda().eval(), pipeline=True))
+    handle = engines[0].prefetch(coords.cuda(), feats.cuda())
+    outs = [e(None, None, handle) for e in engines]
+    torch.cuda.synchronize()
+    alone = engines[1](coords.cuda(), feats.cuda())
+    assert outs[0].shape == outs[1].shape == (len(coords), 8)
+    # same maps, same program; split tiles are summed with float atomics, so two runs differ by a few 1e-4 after 63 layers
+    assert float((outs[1] - alone).abs().max()) <= 2e-3 * float(alone.abs().max())
+    assert float((outs[0] - outs[1]).abs().max()) > 0.05 * float(alone.abs().max())      # different weights
+    xyz, scale, prob = engines[0].decode_separate(outs[0])
+    torch.testing.assert_close(prob, torch.softmax(outs[0][:, 6:8], -1)[:, 1])
+    torch.testing.assert_close(scale, torch.exp(outs[0][:, 3:6]))
+    assert xyz.shape == (len(coords), 3) and bool(((prob >= 0) & (prob <= 1)).all())
