@@ -376,13 +376,31 @@ extern "C" int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, c
     CVB_LAUNCH_CHECK("bp_blockmax_kernel");
     int *ndirty = dirty + nb;
     CVB_CUDA(cudaMemsetAsync(ndirty, 0, 2 * sizeof(int), stream));
+    // 16 CTAs per cluster (non-portable size, one GPC) when the device schedules it and the scene is large; 8 otherwise
+    static int max16 = -1;
+    if (max16 < 0) {
+        max16 = 0;
+        if (cudaFuncSetAttribute(bp_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(16);
+            q.blockDim = dim3(kBpThreads);
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, bp_loop_kernel, &q) == cudaSuccess && nclusters >= 1) max16 = 1;
+        }
+        (void)cudaGetLastError();
+    }
+    const int csize = (max16 == 1 && n >= 100000) ? 16 : kBpCluster;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kBpCluster);
+    cfg.gridDim = dim3(csize);
     cfg.blockDim = dim3(kBpThreads);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kBpCluster;
+    attr[0].val.clusterDim.x = csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
