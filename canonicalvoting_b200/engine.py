@@ -11,11 +11,17 @@ compat package) into a flat program of fused convolution ops executed back to ba
   * `ME.cat(out, skip)` (utils/minkunet.py:153-177) costs nothing: the encoder writes its skip tensor and the
     transposed convolution writes its output into column slices of one pre-allocated buffer;
   * 1x1x1 convolutions (block down-samples, `final`) use the same tensor-core kernel with an identity table;
-  * the head decode (eval_joint.py:173-190) is one kernel.
+  * the 3-channel 5^3 stem runs in the same kernel too (input padded to 4 channels, 8 neighbours gathered per k-block);
+  * every coordinate level and kernel map of the scene comes from ONE enqueue + ONE host synchronisation
+    (cvb200_sc_build_maps); `prefetch()` moves that (and the upload of host tensors) to a worker thread + side stream so
+    that it overlaps the previous scene;
+  * the head decode (eval_joint.py:173-190) is one kernel, optionally also emitting scan_points = coords * res (:193).
 
-    engine = MinkUNetEngine(model)                     # after load_state_dict(...), model.eval()
+    engine = MinkUNetEngine(model, pipeline=True)      # after load_state_dict(...), model.eval()
     feats = engine(coords_int32_cuda, feats_cuda)      # == model(ME.SparseTensor(feats, coords)).F up to TF32 rounding
     xyz, scale, class_pred, prob = engine.predict(coords, feats)
+    nxt = engine.prefetch(next_coords, next_feats)     # host or device tensors; overlaps the calls above
+    xyz, scale, class_pred, prob, points = engine.predict(None, None, nxt, res=0.03)
 """
 import collections
 import ctypes
