@@ -11,7 +11,8 @@ num_rots = 12.  Prints ONE JSON line (rank 0).  DESIGN.md "Measurement" defines 
   value        scenes/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed per step, L2 flushed between
                timed steps, max over ranks
   e2e          scenes/s through the reference-facing API starting from pinned HOST buffers: H2D of coords + feats ->
-               engine -> decode -> hv_cuda.forward (with its geometry sync) -> D2H of the step's result
+               engine -> decode -> hv_cuda.forward (with its geometry sync) -> D2H of the step's result; three scenes in
+               flight (two host syncs per scene leave more bubbles to fill than the resident loop's two scenes)
   passes       the K-step loop runs three times back to back; `value` is the median pass, all three are in passes_ms_per_step
   roofline     the dominant kernel group of the step = the tcgen05 sparse-convolution program of the U-Net:
                algorithmic FLOPs 2 * sum(pairs * cin * cout) / its CUDA-event time, against the measured dense
@@ -231,6 +232,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C5"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--streams", type=int, default=2, help="scenes in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--e2e-streams", type=int, default=3, help="scenes in flight for the end-to-end measurement (more host syncs per scene)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 1)
 
@@ -317,14 +319,15 @@ def main():
     # `--streams` scenes are in flight per GPU: each stream has its own engine instance (activation arena, map side
     # stream, prefetch worker) and is driven by its own host thread; the latency-bound small levels of one scene then
     # overlap the other scene's work.  Stream 0 is the caller's stream.
-    n_streams = max(1, args.streams)
+    n_streams = max(1, args.streams, args.e2e_streams)      # lanes that exist; run_lanes uses the first `active` of them
     engines = [engine] + [MinkUNetEngine(model, NCLASSES, True, pipeline=True) for _ in range(n_streams - 1)]
     lanes = [stream] + [torch.cuda.Stream(dev) for _ in range(n_streams - 1)]
 
-    def run_lanes(fn, k_total):
-        """fn(lane, engine, first_scene, k) on every lane concurrently; returns seconds from the common start to the last
-        lane's end, measured with CUDA events on the lanes' streams."""
+    def run_lanes(fn, k_total, n_streams=None):
+        """fn(lane, engine, first_scene, k) on `n_streams` lanes concurrently; returns seconds from the common start to the
+        last lane's end, measured with CUDA events on the lanes' streams."""
         import threading as th
+        n_streams = max(1, n_streams if n_streams is not None else args.streams)
         start = ev()
         start.record(stream)
         ends = [ev() for _ in range(n_streams)]
@@ -367,7 +370,7 @@ def main():
             step_scene(eng, j, fut)
             fut = nxt
 
-    run_lanes(run_steps, args.warmup * n_streams + n_rot)
+    run_lanes(run_steps, args.warmup * max(1, args.streams) + n_rot)
     barrier()
     import gc
     gc.collect()
@@ -376,7 +379,7 @@ def main():
     with ClockSampler(local) as clk:
         t_attach = time.time()          # let nvidia-smi attach before the timed region -- with the GPU kept busy (an idle
         while time.time() - t_attach < 0.3:   # GPU drops its clocks and the first timed pass pays the ramp-up)
-            run_lanes(run_steps, 2 * n_streams)
+            run_lanes(run_steps, 2 * max(1, args.streams))
         clk.mark()
         for _ in range(3):              # K steps, three times back to back; every pass is reported, the median counts
             passes.append(run_lanes(run_steps, args.steps))
@@ -418,11 +421,11 @@ def main():
             step_e2e(eng, fut)
             fut = nxt
 
-    run_lanes(run_e2e, args.warmup * n_streams)
+    run_lanes(run_e2e, args.warmup * max(1, args.e2e_streams), args.e2e_streams)
     t_e2e = float("inf")
     for _ in range(2):            # two passes of K steps, the steadier one counts (host jitter shows up here: 2 syncs per step)
         barrier()
-        t_e2e = min(t_e2e, run_lanes(run_e2e, args.steps))
+        t_e2e = min(t_e2e, run_lanes(run_e2e, args.steps, args.e2e_streams))
         barrier()
     h2d = coords_h.numel() * 4 + feats_h.numel() * 4
     d2h = 8 + 4 * 5 + 36                               # result + the level sizes of the map builder + the vote grid geometry (hv_cuda.forward)
@@ -469,7 +472,8 @@ def main():
             "passes_ms_per_step": [1e3 * p_ / args.steps for p_ in passes],
             "step_ms_flushed": {"median": float(np.median(step_ms)), "min": float(np.min(step_ms)), "max": float(np.max(step_ms))},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (U-Net) / f32 (vote)",
-            "data": "synthetic", "config": dict(workload_config(args.workload, sc), scenes_in_flight_per_gpu=n_streams),
+            "data": "synthetic", "config": dict(workload_config(args.workload, sc), scenes_in_flight_per_gpu=max(1, args.streams),
+                                              scenes_in_flight_per_gpu_e2e=max(1, args.e2e_streams)),
             "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             # per step: the convolution program (63 persistent conv launches; + the 4-channel pad of the input), 29 kernels of the fused map builder
             # (csrc/sparse_maps.cu), head decode, vote scatter + write-out  (ncu launch list: profiles/r1s_launches_bench_C2.csv)
