@@ -334,15 +334,20 @@ class MinkUNetEngine:
             else:
                 cm = self.build_maps(coords)
             arr, out, keep = self.build(coords, feats.float(), cm)
-            rc = L.cvb200_sc_run_program(arr, len(arr), _stream())
-            _lib.check(rc, "cvb200_sc_run_program")
-            # everything the asynchronous launches touch stays alive until they are known to have completed
-            self._ring.append((keep, main.record_event()))
-            while len(self._ring) > 3:
-                old_keep, done = self._ring.popleft()
-                done.synchronize()
-                del old_keep
+            self.execute(arr, keep)
         return out
+
+    def execute(self, arr, keep):
+        """Launch a program returned by build() on the current stream (asynchronous); `keep` stays referenced until the
+        launches are known to have completed."""
+        L = _lib.load()
+        rc = L.cvb200_sc_run_program(arr, len(arr), _stream())
+        _lib.check(rc, "cvb200_sc_run_program")
+        self._ring.append((keep, torch.cuda.current_stream().record_event()))
+        while len(self._ring) > 3:
+            old_keep, done = self._ring.popleft()
+            done.synchronize()
+            del old_keep
 
     def decode(self, feats, coords=None, res=None):
         """Head decode (eval_joint.py:173-190): features [N, 7*C+1] -> (xyz_pred, scale_pred, class_pred int64, prob_pred).
