@@ -393,7 +393,7 @@ extern "C" int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, c
         }
         (void)cudaGetLastError();
     }
-    const int csize = (max16 == 1 && n >= 100000) ? 16 : kBpCluster;
+    const int csize = (max16 == 1 && n >= 30000) ? 16 : kBpCluster;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(csize);
     cfg.blockDim = dim3(kBpThreads);
