@@ -83,17 +83,17 @@ class MinkUNetBase(nn.Module):
         return self.final(out)
 
 
-class MinkUNet34(MinkUNetBase):
-    LAYERS = (2, 3, 4, 6, 2, 2, 2, 2)                # utils/minkunet.py:193-195
-
-
-class MinkUNet34C(MinkUNet34):
-    PLANES = (32, 64, 128, 256, 256, 128, 96, 96)    # utils/minkunet.py:244-245
-
-
-class MinkUNet14A(MinkUNetBase):
-    LAYERS = (1, 1, 1, 1, 1, 1, 1, 1)
-    PLANES = (32, 64, 128, 256, 128, 128, 96, 96)
+# The model family of utils/minkunet.py:183-245 as a table: depth (blocks per stage) x width variant (planes per stage).
+# Only MinkUNet34C is instantiated by the reference's scripts; MinkUNet14A is the small net of the tests and smoke().
+_DEPTHS = {"14": (1, 1, 1, 1, 1, 1, 1, 1), "18": (2, 2, 2, 2, 2, 2, 2, 2), "34": (2, 3, 4, 6, 2, 2, 2, 2)}
+_ENC = (32, 64, 128, 256)
+_WIDTHS = {"14A": (128, 128, 96, 96), "14B": (128, 128, 128, 128), "14C": (192, 192, 128, 128), "14D": (384, 384, 384, 384),
+           "18A": (128, 128, 96, 96), "18B": (128, 128, 128, 128), "18D": (384, 384, 384, 384),
+           "34A": (256, 128, 64, 64), "34B": (256, 128, 64, 32), "34C": (256, 128, 96, 96)}
+for _d, _layers in _DEPTHS.items():
+    globals()["MinkUNet" + _d] = type("MinkUNet" + _d, (MinkUNetBase,), {"LAYERS": _layers, "__module__": __name__})
+for _v, _dec in _WIDTHS.items():
+    globals()["MinkUNet" + _v] = type("MinkUNet" + _v, (globals()["MinkUNet" + _v[:2]],), {"PLANES": _ENC + _dec, "__module__": __name__})
 
 
 def decode_heads(feats, nclasses=9, log_scale=True):

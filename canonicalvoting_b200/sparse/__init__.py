@@ -6,5 +6,5 @@ utils/minkunet.py:28) binds to it."""
 from . import utils  # noqa: F401
 from .coords import CoordinateManager  # noqa: F401
 from .functional import get_forward_mode, set_forward_mode  # noqa: F401
-from .modules import (BasicBlock, MinkowskiBatchNorm, MinkowskiConvolution, MinkowskiConvolutionTranspose,  # noqa: F401
+from .modules import (BasicBlock, Bottleneck, MinkowskiBatchNorm, MinkowskiConvolution, MinkowskiConvolutionTranspose,  # noqa: F401
                       MinkowskiReLU, SparseTensor, cat)

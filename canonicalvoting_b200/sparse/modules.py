@@ -182,3 +182,32 @@ class BasicBlock(nn.Module):
             residual = self.downsample(x)
         out = out + residual
         return self.relu(out)
+
+
+class Bottleneck(nn.Module):
+    """MinkowskiEngine.modules.resnet_block.Bottleneck [ME-recall]: conv1(1^3)-norm-relu-conv3(3^3, stride)-norm-relu-
+    conv1(1^3, 4x planes)-norm (+downsample) -relu.  Imported by utils/minkunet.py:30 / utils/resnet.py:29 for
+    MinkUNet50/101 and ResNet50/101, which no reference script instantiates (their PLANES are undefined upstream)."""
+    expansion = 4
+    NORM_TYPE = "BN"
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, bn_momentum=0.1, dimension=-1):
+        super().__init__()
+        self.conv1 = MinkowskiConvolution(inplanes, planes, kernel_size=1, dimension=dimension)
+        self.norm1 = MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.conv2 = MinkowskiConvolution(planes, planes, kernel_size=3, stride=stride, dilation=dilation, dimension=dimension)
+        self.norm2 = MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.conv3 = MinkowskiConvolution(planes, planes * self.expansion, kernel_size=1, dimension=dimension)
+        self.norm3 = MinkowskiBatchNorm(planes * self.expansion, momentum=bn_momentum)
+        self.relu = MinkowskiReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        residual = x
+        out = self.relu(self.norm1(self.conv1(x)))
+        out = self.relu(self.norm2(self.conv2(out)))
+        out = self.norm3(self.conv3(out))
+        if self.downsample is not None:
+            residual = self.downsample(x)
+        out = out + residual
+        return self.relu(out)

@@ -116,6 +116,32 @@ def test_minkunet34c_structure_matches_the_reference_model():
     assert (n_conv, n_bn) == (63, 62)
 
 
+def test_model_family_matches_reference_state_dicts():
+    """canonicalvoting_b200/minkunet.py (a table) builds what the reference's utils/minkunet.py builds: state-dict keys,
+    order and shapes of every variant, recorded from the unmodified reference file by tools/make_model_golden.py."""
+    import json
+    import os
+    import canonicalvoting_b200.minkunet as M
+    with open(os.path.join(os.path.dirname(__file__), "golden", "minkunet_state_dicts.json")) as f:
+        golden = json.load(f)
+    assert len(golden) == 11
+    for name, want in golden.items():
+        cls, head = name.split("/")
+        m = getattr(M, cls)(3, 64 if head == "joint" else 8)
+        got = [[k, list(t.shape)] for k, t in m.state_dict().items()]
+        assert got == want, name
+
+
+def test_bottleneck_block_structure():
+    """MinkowskiEngine.modules.resnet_block.Bottleneck (utils/minkunet.py:30): 1^3 -> 3^3 -> 1^3 with 4x expansion."""
+    from MinkowskiEngine.modules.resnet_block import BasicBlock, Bottleneck
+    b = Bottleneck(64, 32, dimension=3)
+    assert Bottleneck.expansion == 4 and BasicBlock.expansion == 1
+    sd = b.state_dict()
+    assert tuple(sd["conv1.kernel"].shape) == (64, 32) and tuple(sd["conv2.kernel"].shape) == (27, 32, 32)
+    assert tuple(sd["conv3.kernel"].shape) == (32, 128) and "norm3.bn.running_var" in sd
+
+
 def test_fast_cpu_port_matches_dict_oracle():
     """The vectorised CPU port timed by bench.py (cpu_baseline of the U-Net half) == the dict-based oracle."""
     from canonicalvoting_b200.minkunet import MinkUNet14A
