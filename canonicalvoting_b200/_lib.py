@@ -28,9 +28,13 @@ SIGNATURES = {
     "cvb200_hv_vote_indices": (ctypes.c_int, [_f, _f, _f, _i64, ctypes.c_float, _i32, ctypes.POINTER(ctypes.c_float),
                                                ctypes.POINTER(_i32), _vp, _vp]),
     "cvb200_hv_theta_table": (ctypes.c_int, [_i32, _f, _f, _vp]),
+    "cvb200_hv_project_y": (ctypes.c_int, [_f, ctypes.POINTER(_i32), _f, _vp, _vp]),
+    "cvb200_hv_proposals_work_bytes": (ctypes.c_size_t, [_i32]),
+    "cvb200_hv_proposals": (ctypes.c_int, [_vp, _i32, _vp, _f, ctypes.POINTER(_i32), ctypes.c_float, ctypes.POINTER(ctypes.c_float),
+                                            _f, _i32, ctypes.c_float, _i32, _f, _f, _vp, _vp, ctypes.c_size_t, _vp]),
 }
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class BpParams(ctypes.Structure):

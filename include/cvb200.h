@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 9
+#define CVB200_ABI_VERSION 10
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -93,6 +93,22 @@ int cvb200_hv_vote_indices(const float *d_points, const float *d_xyz, const floa
  * (hv_cuda_kernel.cu:35-38); d_cos,d_sin [num_rots].  Lets a CPU checker share the
  * exact table. */
 int cvb200_hv_theta_table(int32_t num_rots, float *d_cos, float *d_sin, void *stream);
+
+/* Vote-map proposal sampler of the SUN RGB-D variant (sunrgbd/brnetcanon.py:104-162, HoughVotingModule.forward).
+ * cvb200_hv_project_y: d_max[x*Z+z] = max_y grid_obj[x,y,z], d_arg[x*Z+z] = first y attaining it -- `hv_map.max(1)[0]`
+ * and `torch.argmax(hv_map, 1)` (:120,122) in one pass over the grid. */
+int cvb200_hv_project_y(const float *d_grid_obj, const int32_t dims[3], float *d_max, int32_t *d_arg, void *stream);
+/* One rejection-sampling trial (:133-152).  d_samples int64 [n_samples]: flat (x*Z+z) cells drawn by the caller
+ * (torch.multinomial, :133).  Per sample: y = d_arg[cell], location = (x,y,z)*res + corner (:137), scale =
+ * grid_scale[x,y,z,:] (:138), distance to the nearest of d_seeds [n_seeds,3] (:139); samples closer than `radius` are
+ * kept -- all of them when none is (:142-149) -- and appended IN SAMPLE ORDER to d_loc / d_scale [max_out,3] at row
+ * *d_count, rows >= max_out dropped (:154-159); *d_count += kept (device int32, may pass max_out).  Asynchronous.
+ *   d_work >= cvb200_hv_proposals_work_bytes(n_samples) bytes */
+size_t cvb200_hv_proposals_work_bytes(int32_t n_samples);
+int cvb200_hv_proposals(const int64_t *d_samples, int32_t n_samples, const int32_t *d_arg, const float *d_grid_scale,
+                        const int32_t dims[3], float res, const float corner[3], const float *d_seeds, int32_t n_seeds,
+                        float radius, int32_t max_out, float *d_loc, float *d_scale, int32_t *d_count, void *d_work,
+                        size_t work_bytes, void *stream);
 
 /* ------------------------------------------------------- candidate loop / back-projection ---- */
 
