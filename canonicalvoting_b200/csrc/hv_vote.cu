@@ -5,8 +5,9 @@
 //   (houghvoting/src/hv_cuda_kernel.cu:12-97, :100-119, :121-165)
 //   hv_cuda_backward_kernel / hv_cuda_backward (:168-261, :265-302)
 // with a different decomposition (see DESIGN.md "vote op" and the "forward" section below):
-// a counting sort of the votes by grid cell followed by a per-voxel gather, instead of 48
-// float atomics per vote; outputs are written exactly once and never memset.
+// one work item per (point, theta), the six channels of a voxel accumulated in one 32-byte workspace
+// sector by two vector reductions per corner (16 per vote instead of 48 scalar atomics), and a
+// write-out pass that normalises, writes every output once and leaves the workspace zero again.
 //
 // Float contract: the integer voxel index of a vote must be bit-identical to the
 // reference's sm_100 build.  vote_center() spells out that build's exact operation
