@@ -422,3 +422,25 @@ def test_per_category_engines_share_one_coordinate_map():
     torch.testing.assert_close(prob, torch.softmax(outs[0][:, 6:8], -1)[:, 1])
     torch.testing.assert_close(scale, torch.exp(outs[0][:, 3:6]))
     assert xyz.shape == (len(coords), 3) and bool(((prob >= 0) & (prob <= 1)).all())
+
+
+@pytest.mark.parametrize("variant", ["MinkUNet14D", "MinkUNet18B", "MinkUNet34B"])
+def test_engine_runs_the_other_family_members(variant):
+    """The fused engine is built from the module tree, not from a MinkUNet34C layer list: wide (384-channel, three channel
+    splits), shallow and narrow-decoder (32-channel) variants of utils/minkunet.py:208-245 against the fp32 module path."""
+    import canonicalvoting_b200.minkunet as M
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200.engine import MinkUNetEngine
+    torch.manual_seed(3)
+    coords, feats = _scene(n=2500, G=40, batch=1, cin=3, seed=21)
+    model = getattr(M, variant)(3, 64).cuda().eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.8, 1.2)
+        ME.set_forward_mode("fp32")
+        ref = model(ME.SparseTensor(feats, coords, device="cuda")).F
+    got = MinkUNetEngine(model)(coords.cuda(), feats.cuda())
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert got.shape == ref.shape and float((got - ref).abs().max()) <= 2e-2 * scale
