@@ -42,3 +42,20 @@ def test_nms_edge_cases():
     assert got.cpu().tolist() == O.nms_per_class(boxes, scores, classes, 9, 0.3)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         obb.nms_per_class(torch.from_numpy(boxes), torch.from_numpy(scores), torch.from_numpy(classes), 9)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_detection_metric_on_device_ious_matches_oracle(seed):
+    """canonicalvoting_b200/evaluate.py with its default IoU source (obb.iou_matrix on the device, one call per scene
+    and class) against oracle/calc_map.py (the reference's per-pair loop, utils/calc_map.py:78-168)."""
+    from canonicalvoting_b200 import evaluate as E
+    from oracle import calc_map as OM
+    from tests.test_oracle_map import random_eval_case
+    pred_all, gt_all = random_eval_case(seed)
+    gt_all = {s: [(c, b.astype(np.float32)) for c, b in v] for s, v in gt_all.items()}     # the device takes float32 boxes
+    for thresh in (0.25, 0.5):
+        want = OM.compute_map(pred_all, gt_all, thresh)
+        got = E.compute_map(pred_all, gt_all, thresh)
+        assert list(got) == list(want)
+        for k in want:
+            np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64), np.asarray(want[k], dtype=np.float64), rtol=0, atol=1e-12, err_msg=k)
