@@ -67,7 +67,7 @@ struct PsUnit {
     int row0, n0, kb0, kb1, pieces, split_tile;
 };
 
-__device__ __forceinline__ PsUnit ps_unit(const PsPlan &P, int u) {
+__host__ __device__ __forceinline__ PsUnit ps_unit(const PsPlan &P, int u) {
     int tile, piece, pieces;
     if (u < P.n_whole) {
         tile = u; piece = 0; pieces = 1;
@@ -623,6 +623,29 @@ extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) 
     return 0;
 }
 
+
+/* Host-only inspection of the work plan of one convolution (no device work): what the persistent kernel's CTAs will walk.
+ * h_plan[12] = {n_tiles, n_splits, n_whole, ks, n_units, total_kb, cblocks, stages, nc, acc_stride, tmem_cols, smem_bytes};
+ * h_units (may be NULL) receives n_units rows {row0, n0, kb0, kb1, pieces, split_tile}, at most max_units of them. */
+extern "C" int cvb200_sc_conv_plan(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units,
+                                   int32_t max_units) {
+    using namespace cvb200;
+    CVB_REQUIRE(h_plan && n_out > 0 && n_out < (1LL << 31) && cin > 0 && cin % kPsKB == 0 && cout >= 16 && cout <= 1024 && cout % 16 == 0 && k3 > 0,
+                CVB200_EINVAL, "sc_conv_plan: needs n_out > 0, cin %% 32 == 0, cout %% 16 == 0, 16 <= cout <= 1024 (got %lld, %d, %d, %d)",
+                (long long)n_out, cin, cout, k3);
+    PsPlan P;
+    int ctas_per_sm = 1;
+    ps_plan(n_out, cin, cout, k3, &P, &ctas_per_sm);
+    const int v[12] = {P.n_tiles, P.n_splits, P.n_whole, P.ks, P.n_units, P.total_kb, P.cblocks, P.stages, P.nc, P.acc_stride, P.tmem_cols,
+                       1024 + 16384 + P.stages * (kPsM * 128 + P.nc * 128)};
+    for (int i = 0; i < 12; i++) h_plan[i] = v[i];
+    for (int u = 0; h_units && u < P.n_units && u < max_units; u++) {
+        const PsUnit U = ps_unit(P, u);
+        const int w[6] = {U.row0, U.n0, U.kb0, U.kb1, U.pieces, U.split_tile};
+        for (int i = 0; i < 6; i++) h_units[6 * u + i] = w[i];
+    }
+    return 0;
+}
 
 /* Measurement aid: switch off parts of the persistent kernel (results become garbage): 1 no gather copies, 2 no zero-fill
  * copies, 4 no MMA, 8 no weight TMA.  0 = normal operation. */

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 10
+#define CVB200_ABI_VERSION 11
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -227,6 +227,12 @@ int cvb200_sc_set_conv_debug(int32_t mask);
 /* Measurement aid: device buffer of 3 x 768 int64 that receives clock64 stamps (before wait, after wait, after issue) of the
  * first 256 k-blocks of CTA 0 for the MMA thread, one gather warp and the weight-TMA thread; NULL switches it off. */
 int cvb200_sc_set_conv_trace(void *d_trace);
+
+/* Host-only inspection of the work plan of one tensor-core convolution (no device work, no GPU needed): the units the
+ * persistent kernel's CTAs walk.  h_plan[12] = {n_tiles, n_splits, n_whole, ks, n_units, total_kb, cblocks, stages, nc,
+ * acc_stride, tmem_cols, smem_bytes}; h_units (may be NULL) receives min(n_units, max_units) rows {row0, n0, kb0, kb1, pieces,
+ * split_tile}.  Used by the CPU tests to check that every (row tile, channel block, k-block) is covered exactly once. */
+int cvb200_sc_conv_plan(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units, int32_t max_units);
 
 /* On-device voxelisation = ME.utils.sparse_quantize (utils/dataloader.py:197, sunrgbd/brnetcanon.py:218): d_xyz float32 [n,3];
  * voxel = floor(p / quantization_size) evaluated in float32 (quantization_size <= 0: floor(p)); d_voxel int32 [n,4] receives
