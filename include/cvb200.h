@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 11
+#define CVB200_ABI_VERSION 12
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -233,6 +233,16 @@ int cvb200_sc_set_conv_trace(void *d_trace);
  * acc_stride, tmem_cols, smem_bytes}; h_units (may be NULL) receives min(n_units, max_units) rows {row0, n0, kb0, kb1, pieces,
  * split_tile}.  Used by the CPU tests to check that every (row tile, channel block, k-block) is covered exactly once. */
 int cvb200_sc_conv_plan(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units, int32_t max_units);
+
+/* EXPERIMENTAL (round-2 work item, not on the product path, not yet run on a GPU): bf16 variant of the persistent tensor-core
+ * convolution.  d_in bf16 [n_in, ldi], d_res bf16 [n_out, ldr] (may be NULL), d_out bf16 [n_out, ldo] (float32 when out_f32),
+ * d_bias float32 [cout] (may be NULL); d_w bf16 [cout][k3 * cin]: the weights with the contraction axis flattened
+ * (w[co][k * cin + c] = kernel[k][c][co]); d_nbr int32 [n_out, k3].  cin % 32 == 0, cout % 16 == 0; strides in elements. */
+int cvb200_sc_conv_forward_bf16(const void *d_in, int64_t n_in, int32_t ldi, int32_t cin, const void *d_w, int32_t cout,
+                                const int32_t *d_nbr, int64_t n_out, int32_t k3, const float *d_bias, const void *d_res, int32_t ldr,
+                                int32_t relu, void *d_out, int32_t ldo, int32_t out_f32, void *stream);
+/* Host-only: its work plan, same layout as cvb200_sc_conv_plan (total_kb counts k-blocks of 64 elements of the flattened axis). */
+int cvb200_sc_conv_plan_bf16(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units, int32_t max_units);
 
 /* On-device voxelisation = ME.utils.sparse_quantize (utils/dataloader.py:197, sunrgbd/brnetcanon.py:218): d_xyz float32 [n,3];
  * voxel = floor(p / quantization_size) evaluated in float32 (quantization_size <= 0: floor(p)); d_voxel int32 [n,4] receives
