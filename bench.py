@@ -35,6 +35,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 NCLASSES = 9
+# DRAM bytes per call of the vote op from the ncu --set full capture of round 1 (scatter 21.03 MB read; write-out 67.13 MB read +
+# 15.25 MB written before the kernel ended), C2 scene only; None where no capture exists
+VOTE_DRAM_BYTES_NCU = {"C2": 21029376 + 8192 + 67128832 + 15247104}
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -486,7 +489,9 @@ def main():
                          "algorithmic_flops": flops, "kernel_ms": unet_med,
                          "vote": {"bound": "hbm", "achieved": vote_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": vote_gbs / hbm_gbs,
                                   "kernel": "hv_scatter_kernel + hv_finalize_kernel", "algorithmic_bytes": vbytes,
-                                  "kernel_ms": vote_med}},
+                                  "kernel_ms": vote_med, "traffic": VOTE_DRAM_BYTES_NCU.get(args.workload),
+                                  "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two kernels, one ncu --set full "
+                                                    "capture (profiles/r1s_ncu_full_vote_raw.csv); outputs still in L2 at kernel end are not in it"}},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
         }
