@@ -48,6 +48,20 @@ class SparseTensor:
     def shape(self):
         return self._F.shape
 
+    @property
+    def decomposed_coordinates_and_features(self):
+        """(list of [Ni,3] coordinates, list of [Ni,C] features), one entry per batch index (sunrgbd/brnetcanon.py:227,318);
+        rows keep their order [ME-recall]."""
+        return decompose(self.C, self._F)
+
+    @property
+    def decomposed_coordinates(self):
+        return decompose(self.C, self._F)[0]
+
+    @property
+    def decomposed_features(self):
+        return decompose(self.C, self._F)[1]
+
     def _like(self, feats, tensor_stride=None):
         return SparseTensor(feats, coordinate_manager=self.coordinate_manager,
                             tensor_stride=self.tensor_stride if tensor_stride is None else tensor_stride)
@@ -59,6 +73,17 @@ class SparseTensor:
 
     def __repr__(self):
         return "SparseTensor(N=%d, C=%d, tensor_stride=%d)" % (self._F.shape[0], self._F.shape[1], self.tensor_stride)
+
+
+def decompose(coords, feats):
+    """Split batched rows by the batch column of `coords` [N,4]: ([coords_b [Nb,3]], [feats_b [Nb,C]]) for b = 0..B-1."""
+    if coords.shape[0] == 0:
+        return [], []
+    b = coords[:, 0].long()
+    nb = int(b.max()) + 1
+    order = torch.argsort(b, stable=True)                 # rows of one scene stay in their input order
+    counts = torch.bincount(b, minlength=nb).tolist()
+    return list(torch.split(coords[order, 1:], counts)), list(torch.split(feats[order], counts))
 
 
 def cat(*tensors):

@@ -142,6 +142,21 @@ def test_bottleneck_block_structure():
     assert tuple(sd["conv3.kernel"].shape) == (32, 128) and "norm3.bn.running_var" in sd
 
 
+def test_decompose_splits_rows_by_batch_in_order():
+    """SparseTensor.decomposed_coordinates_and_features (sunrgbd/brnetcanon.py:227): per-scene lists, row order kept."""
+    from canonicalvoting_b200.sparse.modules import decompose
+    g = torch.Generator().manual_seed(0)
+    coords = torch.randint(0, 50, (40, 4), generator=g).int()
+    coords[:, 0] = torch.randint(0, 3, (40,), generator=g).int()
+    feats = torch.randn(40, 5, generator=g)
+    cs, fs = decompose(coords, feats)
+    assert len(cs) == len(fs) == 3
+    for b in range(3):
+        m = coords[:, 0] == b
+        assert torch.equal(cs[b], coords[m][:, 1:]) and torch.equal(fs[b], feats[m])
+    assert decompose(coords[:0], feats[:0]) == ([], [])
+
+
 def test_fast_cpu_port_matches_dict_oracle():
     """The vectorised CPU port timed by bench.py (cpu_baseline of the U-Net half) == the dict-based oracle."""
     from canonicalvoting_b200.minkunet import MinkUNet14A
