@@ -47,9 +47,9 @@ def test_nms_edge_cases():
 @pytest.mark.parametrize("seed", [0, 3])
 def test_detection_metric_on_device_ious_matches_oracle(seed):
     """canonicalvoting_b200/evaluate.py with its default IoU source (obb.iou_matrix on the device, one call per scene
-    and class) against oracle/calc_map.py (the reference's per-pair loop, utils/calc_map.py:78-168)."""
+    and class) against oracle/detection_metric.py (the reference's per-pair loop, utils/calc_map.py:78-168)."""
     from canonicalvoting_b200 import evaluate as E
-    from oracle import calc_map as OM
+    from oracle import detection_metric as OM
     from tests.test_oracle_map import random_eval_case
     pred_all, gt_all = random_eval_case(seed)
     gt_all = {s: [(c, b.astype(np.float32)) for c, b in v] for s, v in gt_all.items()}     # the device takes float32 boxes

@@ -1,6 +1,6 @@
 """CPU end-to-end check of the oracle chain on planted objects: vote (oracle/hv_oracle.c) -> candidate loop with the LCC
 back-projection check (oracle/candidate_loop.py) -> per-class OBB NMS (oracle/obb_nms.py) -> detection metric
-(oracle/calc_map.py) against the ground-truth boxes of the synthetic scene.  The synthetic per-point predictions are the
+(oracle/detection_metric.py) against the ground-truth boxes of the synthetic scene.  The synthetic per-point predictions are the
 planted objects' LCC coordinates + noise, so every box the loop accepts must be one of them (precision 1 at IoU 0.5), in the
 yaw convention of eval_joint.py:213-215,299.  This is what ties the four oracles -- each pinned separately -- together."""
 import numpy as np
@@ -8,7 +8,7 @@ import pytest
 
 from canonicalvoting_b200 import evaluate as E
 from canonicalvoting_b200 import synthetic
-from oracle import calc_map as OM
+from oracle import detection_metric as OM
 from oracle import candidate_loop as CL
 from oracle import hv_oracle as O
 from oracle import obb_nms as ON
@@ -27,7 +27,7 @@ def test_accepted_boxes_are_the_planted_objects(n, G, R, seed):
     gt = [(E.CATEGORIES[k], E.gt_box(c[0], c[1], c[2], yaw, h[0], h[1], h[2])) for c, h, yaw, k in sc["boxes"]]
     assert len(dets) >= 3 and iters > len(dets)
     for thresh in (0.25, 0.5):
-        rec, prec, ap = OM.eval_det({"scene": dets}, {"scene": gt}, thresh)
+        rec, prec, ap = OM.evaluate({"scene": dets}, {"scene": gt}, thresh)
         n_tp = sum(int(round(rec[c][-1] * sum(1 for g in gt if g[0] == c))) for c in rec if not np.isscalar(rec[c]))
         assert n_tp == len(dets), "an accepted box is not a planted object at IoU %.2f" % thresh
         for c in prec:
