@@ -56,3 +56,47 @@ def train_step(model, optimizer, batch, device):
 def shard_scenes(n_scenes, rank, world):
     """Scene i -> rank i mod world."""
     return [i for i in range(n_scenes) if i % world == rank]
+
+
+# ---- schedules of the training script (train_joint.py:100-138,200-206,224-225; config/config.yaml:30-36)
+def learning_rate(epoch, base=1e-3, decay_steps=(80, 120, 160), decay_rates=(0.1, 0.1, 0.1)):
+    """get_current_lr (train_joint.py:128-133): the base rate times every decay factor whose epoch has been reached."""
+    lr = base
+    for step, rate in zip(decay_steps, decay_rates):
+        if epoch >= step:
+            lr *= rate
+    return lr
+
+
+def adjust_learning_rate(optimizer, epoch, **schedule):
+    """train_joint.py:135-138."""
+    lr = learning_rate(epoch, **schedule)
+    for group in optimizer.param_groups:
+        group["lr"] = lr
+    return lr
+
+
+def bn_momentum(epoch, init=0.5, floor=0.001, decay_step=20, decay_rate=0.5):
+    """The `bn_lbmd` lambda of train_joint.py:224: init * rate^(epoch // step), not below the floor."""
+    return max(init * decay_rate ** int(epoch / decay_step), floor)
+
+
+class BNMomentumScheduler:
+    """train_joint.py:100-125.  Like the reference's setter (:92-97) it writes `momentum` on the MinkowskiBatchNorm WRAPPER
+    modules; the wrapped `bn` (nn.BatchNorm1d) keeps its own momentum of 0.1, which is what the reference observably trains
+    with."""
+
+    def __init__(self, model, bn_lambda=bn_momentum, last_epoch=-1):
+        if not isinstance(model, torch.nn.Module):
+            raise RuntimeError("Class '%s' is not a PyTorch nn Module" % type(model).__name__)
+        self.model, self.lmbd = model, bn_lambda
+        self.step(last_epoch + 1)
+        self.last_epoch = last_epoch
+
+    def step(self, epoch=None):
+        epoch = self.last_epoch + 1 if epoch is None else epoch
+        self.last_epoch = epoch
+        value = self.lmbd(epoch)
+        for m in self.model.modules():
+            if isinstance(m, ME.MinkowskiBatchNorm):
+                m.momentum = value

@@ -123,5 +123,23 @@ def test_joint_loss_matches_the_reference_script():
     out = torch.from_numpy(g["out"]).requires_grad_(True)
     loss = train.joint_loss(out, torch.from_numpy(g["xyz"]), torch.from_numpy(g["scale"]), torch.from_numpy(g["cls"]))
     loss.backward()
-    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
     np.testing.assert_allclose(out.grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
+
+
+def test_schedules_match_the_reference_script():
+    """get_current_lr (train_joint.py:128-133) and the BN-momentum lambda (:224) executed verbatim for epochs 0..200."""
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200 import train
+    g = np.load(os.path.join(GOLD, "refpy_schedules.npz"))
+    for e, lr, bn in zip(g["epochs"], g["lr"], g["bn"]):
+        assert train.learning_rate(int(e)) == lr and train.bn_momentum(int(e)) == bn
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    assert train.adjust_learning_rate(opt, 125) == opt.param_groups[0]["lr"] == g["lr"][125]
+    model = torch.nn.Sequential(ME.MinkowskiBatchNorm(8), torch.nn.ReLU())
+    sched = train.BNMomentumScheduler(model, last_epoch=39)
+    assert model[0].momentum == g["bn"][40] and model[0].bn.momentum == 0.1          # the wrapped BatchNorm1d is not reached
+    sched.step()
+    assert sched.last_epoch == 40 and model[0].momentum == g["bn"][40]
+    sched.step(60)
+    assert model[0].momentum == g["bn"][60]

@@ -14,6 +14,7 @@ repository except the resulting numbers.
     utils/calc_map.py:40-71,78-168  voc_ap, eval_det_cls (IoU injected likewise)          -> tests/golden/refpy_metric.npz
     train_joint.py:253-282          joint loss of the training step (xyz_component_weights 1,1,1; factors of config.yaml)
                                                                                           -> tests/golden/refpy_loss.npz
+    train_joint.py:128-133,200-206,224  learning-rate and BN-momentum schedules           -> tests/golden/refpy_schedules.npz
     sunrgbd/brnetcanon.py:119-161   vote-map proposal sampler (torch.multinomial replaced by recorded draws; :86-91 unravel_index)
                                                                                           -> tests/golden/refpy_proposals.npz
 
@@ -143,6 +144,17 @@ def main():
     np.savez_compressed(os.path.join(OUT, "refpy_loss.npz"), out=out_f.detach().numpy(), xyz=xyz_l.numpy(), scale=scale_l.numpy(), cls=cls_l.numpy(),
                         loss=float(loss), grad=out_f.grad.numpy())
     print("loss", float(loss))
+
+    # ---- schedules: get_current_lr (train_joint.py:128-133) and the bn_lbmd lambda (:224) with the constants of :200-206 / config.yaml
+    tj = open(os.path.join(REF, "train_joint.py")).read()
+    senv = {"BN_MOMENTUM_INIT": 0.5, "BN_MOMENTUM_MAX": 0.001, "BN_DECAY_STEP": 20, "BN_DECAY_RATE": 0.5, "BASE_LEARNING_RATE": 1e-3,
+            "LR_DECAY_STEPS": [80, 120, 160], "LR_DECAY_RATES": [0.1, 0.1, 0.1]}
+    exec(re.search(r"^def get_current_lr\(.*?(?=^\S)", tj, re.M | re.S).group(0), senv)
+    exec(textwrap.dedent(re.search(r"^\s*bn_lbmd = lambda.*$", tj, re.M).group(0)), senv)
+    epochs = np.arange(0, 201)
+    np.savez_compressed(os.path.join(OUT, "refpy_schedules.npz"), epochs=epochs, lr=np.array([senv["get_current_lr"](int(e)) for e in epochs]),
+                        bn=np.array([senv["bn_lbmd"](int(e)) for e in epochs]))
+    print("schedules", senv["get_current_lr"](130), senv["bn_lbmd"](45))
 
     # ---- proposal sampler: the body of HoughVotingModule.forward after the vote, draws injected
     from tests.test_oracle_proposals import vote_case
