@@ -143,3 +143,22 @@ def test_schedules_match_the_reference_script():
     assert sched.last_epoch == 40 and model[0].momentum == g["bn"][40]
     sched.step(60)
     assert model[0].momentum == g["bn"][60]
+
+
+def test_per_category_loop_variant_matches_eval_separate():
+    """eval_separate.py:203-258 executed verbatim (zeroes [c-2, c+2), no class vote) vs the oracle with elim_hi_inclusive=False --
+    the switch cvb200_bp_params carries for this script."""
+    g = np.load(os.path.join(GOLD, "refpy_loop_sep.npz"))
+    sc = synthetic.make_scene(int(g["n"]), int(g["G"]), int(g["R"]), seed=int(g["seed"]), n_objects=int(g["n_objects"]))
+    go, gr, gs = O.forward(sc["points"], sc["xyz"], sc["scale"], sc["obj"], np.float32(RES), int(g["R"]), threads=1)
+    assert hashlib.sha1(go.tobytes() + gr.tobytes() + gs.tobytes()).hexdigest() == str(g["grids_sha1"])
+    grid = go.copy()
+    b, s, c, it = CL.loop_numpy(grid, gr, gs, sc["points"], sc["xyz"], sc["obj"], sc["class_pred"], RES, thresh_high=60.0, elim_hi_inclusive=False)
+    assert len(b) == len(g["boxes"]) >= 3
+    np.testing.assert_allclose(b, g["boxes"], rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(np.asarray(s, np.float32), g["scores"].astype(np.float32))
+    np.testing.assert_array_equal(np.flatnonzero(grid.reshape(-1) != go.reshape(-1)).astype(np.int32), g["zeroed"])
+    # the inclusive variant (eval_joint.py) zeroes a different set: the switch matters on this scene
+    grid2 = go.copy()
+    CL.loop_numpy(grid2, gr, gs, sc["points"], sc["xyz"], sc["obj"], sc["class_pred"], RES, thresh_high=60.0)
+    assert not np.array_equal(grid2, grid)
