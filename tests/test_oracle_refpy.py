@@ -146,7 +146,7 @@ def test_schedules_match_the_reference_script():
 
 
 def test_per_category_loop_variant_matches_eval_separate():
-    """eval_separate.py:203-258 executed verbatim (zeroes [c-2, c+2), no class vote) vs the oracle with elim_hi_inclusive=False --
+    """eval_separate.py:203-260 executed verbatim (zeroes [c-2, c+2), no class vote) vs the oracle with elim_hi_inclusive=False --
     the switch cvb200_bp_params carries for this script."""
     g = np.load(os.path.join(GOLD, "refpy_loop_sep.npz"))
     sc = synthetic.make_scene(int(g["n"]), int(g["G"]), int(g["R"]), seed=int(g["seed"]), n_objects=int(g["n_objects"]))

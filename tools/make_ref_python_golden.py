@@ -10,7 +10,7 @@ repository except the resulting numbers.
 
     eval_joint.py:173-190   head decode                       -> tests/golden/refpy_decode.npz
     eval_joint.py:196-268   candidate loop (+ :19-22 thresholds, :60-66 unravel_index)   -> tests/golden/refpy_loop_*.npz
-    eval_separate.py:203-258 the per-category variant of the loop (zeroes [c-2, c+2), threshold 60 hard-coded, no class vote)
+    eval_separate.py:203-260 the per-category variant of the loop (zeroes [c-2, c+2), threshold 60 hard-coded, no class vote)
                                                               -> tests/golden/refpy_loop_sep.npz
     eval_joint.py:75-89     nms  (IoU injected: oracle/obb_nms.get_iou_obb, shapely is absent)
     utils/calc_map.py:40-71,78-168  voc_ap, eval_det_cls (IoU injected likewise)          -> tests/golden/refpy_metric.npz
@@ -101,13 +101,13 @@ def main():
             picks = {int(k): [int(i) for i in env["nms"](many[cl_ == k], sc_[cl_ == k], 0.3)] for k in np.unique(cl_)}
             np.savez_compressed(os.path.join(OUT, "refpy_nms.npz"), boxes=many, scores=sc_, classes=cl_,
                                 picks=np.array([(k, i) for k, v in picks.items() for i in v], np.int64))
-    # ---- the loop of eval_separate.py (:203-258): names as the script holds them at :188-201
+    # ---- the loop of eval_separate.py (:203-260): names as the script holds them at :188-201
     senv2 = dict(env)
     senv2.update(scannet_res=0.03, elimination=2,
                  bbox_raw=torch.tensor([[1, 1, -1, -1, 1, 1, -1, -1], [1, 1, 1, 1, -1, -1, -1, -1], [1, -1, -1, 1, 1, -1, -1, 1]]).float().T)
     # (bbox_raw above is the value eval_separate.py builds at :148-150 with l = h = w = 2, scannet_res the one of :151)
     sep_loop = make_function("ref_loop_sep", ["grid_obj", "grid_rot", "grid_scale", "scan_points", "corners", "xyz_pred", "prob_pred"],
-                             "boxes = []\nscores = []\nprobs = []\n" + cut("eval_separate.py", 203, 258), "boxes, scores, grid_obj", senv2)
+                             "boxes = []\nscores = []\nprobs = []\n" + cut("eval_separate.py", 203, 260), "boxes, scores, grid_obj", senv2)
     c = dict(n=8000, G=40, R=120, seed=3, n_objects=6)
     sc = synthetic.make_scene(c["n"], c["G"], c["R"], seed=c["seed"], n_objects=c["n_objects"])
     go, gr, gs = O.forward(sc["points"], sc["xyz"], sc["scale"], sc["obj"], np.float32(0.03), c["R"], threads=1)
