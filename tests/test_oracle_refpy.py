@@ -162,3 +162,27 @@ def test_per_category_loop_variant_matches_eval_separate():
     grid2 = go.copy()
     CL.loop_numpy(grid2, gr, gs, sc["points"], sc["xyz"], sc["obj"], sc["class_pred"], RES, thresh_high=60.0)
     assert not np.array_equal(grid2, grid)
+
+
+@pytest.mark.parametrize("name", ["MinkUNet14A", "MinkUNet34C"])
+def test_unet_wiring_matches_the_reference_forward(name):
+    """utils/minkunet.py:122-180 -- the reference class's own forward(), run on CPU with its convolutions routed to the oracle
+    (tools/make_ref_python_golden.py::unet_wiring_golden) -- vs OracleNet on this repository's model built from the same
+    seed: layer order, skip connections and concatenation order of the two restatements are the reference's."""
+    import canonicalvoting_b200.minkunet as M
+    from oracle import sparse_oracle as SO
+    g = np.load(os.path.join(GOLD, "refpy_unet_wiring.npz"))
+    torch.manual_seed(11)
+    model = getattr(M, name)(3, 20).eval()
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.1, generator=gen)
+                m.running_var.uniform_(0.5, 1.5, generator=gen)
+    coords, feats = torch.from_numpy(g[name + "_coords"]), torch.from_numpy(g[name + "_feats"])
+    with torch.no_grad():
+        y = SO.OracleNet(model).forward(coords, feats)
+    want = g[name + "_out"]
+    assert y.shape == want.shape
+    np.testing.assert_allclose(y.numpy(), want, rtol=0, atol=1e-5 * float(np.abs(want).max()))

@@ -17,6 +17,9 @@ repository except the resulting numbers.
     train_joint.py:253-282          joint loss of the training step (xyz_component_weights 1,1,1; factors of config.yaml)
                                                                                           -> tests/golden/refpy_loss.npz
     train_joint.py:128-133,200-206,224  learning-rate and BN-momentum schedules           -> tests/golden/refpy_schedules.npz
+    utils/minkunet.py:122-180       MinkUNetBase.forward, the wiring of the U-Net: the reference class (imported unmodified on the
+                                    MinkowskiEngine/ compat package) runs on CPU with the sparse ops routed to the convolution oracle
+                                                                                          -> tests/golden/refpy_unet_wiring.npz
     sunrgbd/brnetcanon.py:119-161   vote-map proposal sampler (torch.multinomial replaced by recorded draws; :86-91 unravel_index)
                                                                                           -> tests/golden/refpy_proposals.npz
 
@@ -66,6 +69,73 @@ def reference_env():
         exec(m.group(0), env)
     env["get_iou_obb"] = ON.get_iou_obb
     return env
+
+
+class CpuSparse:
+    """Stand-in for ME.SparseTensor on the CPU: features + the shared {tensor stride: coordinates} table."""
+
+    def __init__(self, F, cm, ts):
+        self.F, self.coordinate_manager, self.tensor_stride = F, cm, ts
+
+    def _like(self, F, tensor_stride=None):
+        return CpuSparse(F, self.coordinate_manager, self.tensor_stride if tensor_stride is None else tensor_stride)
+
+    def __add__(self, other):
+        return self._like(self.F + other.F)
+
+    __iadd__ = __add__
+
+
+def unet_wiring_golden():
+    """Import utils/minkunet.py of the reference UNMODIFIED (on this repository's MinkowskiEngine/ compat package, whose module
+    constructors work on the CPU), route the two convolution module types to oracle/sparse_oracle.py for the duration of the
+    call, and run the reference's own forward().  What this pins: the order of layers, the skip connections and the
+    concatenation order of MinkUNetBase.forward (utils/minkunet.py:122-180) as OracleNet / canonicalvoting_b200.minkunet
+    restate them.  What it cannot pin: MinkowskiEngine's own operator semantics (the oracle's)."""
+    sys.path.insert(1, REF)
+    import utils.minkunet as ref_unet
+    from canonicalvoting_b200.sparse import modules as M
+    from oracle import sparse_oracle as SO
+
+    def conv_forward(self, x):
+        w = self.kernel.detach()
+        b = self.bias.detach() if self.bias is not None else None
+        C, ts = x.coordinate_manager, x.tensor_stride
+        if self.kernel_size == 1:
+            return x._like(x.F @ w + (b if b is not None else 0))
+        if self.stride == 2:
+            coarse, out = SO.conv_down(C[ts], x.F, w, ts, b)
+            C[2 * ts] = coarse
+            return x._like(out, 2 * ts)
+        return x._like(SO.conv_same(C[ts], x.F, w, self.kernel_size, ts, b))
+
+    def convtr_forward(self, x):
+        C, ts = x.coordinate_manager, x.tensor_stride
+        return x._like(SO.conv_up(C[ts // 2], x.F, self.kernel.detach(), ts, self.bias.detach() if self.bias is not None else None), ts // 2)
+
+    saved = (M.MinkowskiConvolution.forward, M.MinkowskiConvolutionTranspose.forward)
+    M.MinkowskiConvolution.forward, M.MinkowskiConvolutionTranspose.forward = conv_forward, convtr_forward
+    try:
+        out = {}
+        for name, n, G in (("MinkUNet14A", 500, 20), ("MinkUNet34C", 400, 18)):
+            torch.manual_seed(11)
+            model = getattr(ref_unet, name)(3, 20).eval()
+            g = torch.Generator().manual_seed(5)
+            with torch.no_grad():
+                for m in model.modules():
+                    if isinstance(m, torch.nn.BatchNorm1d):
+                        m.running_mean.normal_(0, 0.1, generator=g)
+                        m.running_var.uniform_(0.5, 1.5, generator=g)
+            lin = torch.randperm(G ** 3, generator=g)[:n]
+            coords = torch.stack([lin % 2, lin // (G * G), (lin // G) % G, lin % G], 1).int()      # two scenes in the batch column
+            feats = torch.randn(n, 3, generator=g)
+            with torch.no_grad():
+                y = model(CpuSparse(feats, {1: coords}, 1)).F
+            print("unet wiring", name, tuple(y.shape), float(y.abs().max()))
+            out.update({name + "_coords": coords.numpy(), name + "_feats": feats.numpy(), name + "_out": y.numpy()})
+        np.savez_compressed(os.path.join(OUT, "refpy_unet_wiring.npz"), **out)
+    finally:
+        M.MinkowskiConvolution.forward, M.MinkowskiConvolutionTranspose.forward = saved
 
 
 def main():
@@ -177,6 +247,9 @@ def main():
     np.savez_compressed(os.path.join(OUT, "refpy_schedules.npz"), epochs=epochs, lr=np.array([senv["get_current_lr"](int(e)) for e in epochs]),
                         bn=np.array([senv["bn_lbmd"](int(e)) for e in epochs]))
     print("schedules", senv["get_current_lr"](130), senv["bn_lbmd"](45))
+
+    # ---- U-Net wiring: the reference's MinkUNetBase.forward on CPU
+    unet_wiring_golden()
 
     # ---- proposal sampler: the body of HoughVotingModule.forward after the vote, draws injected
     from tests.test_oracle_proposals import vote_case
