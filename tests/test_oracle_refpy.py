@@ -186,3 +186,13 @@ def test_unet_wiring_matches_the_reference_forward(name):
     want = g[name + "_out"]
     assert y.shape == want.shape
     np.testing.assert_allclose(y.numpy(), want, rtol=0, atol=1e-5 * float(np.abs(want).max()))
+
+
+def test_collate_matches_the_reference_function():
+    """train_joint.py:78-90 `collate_fn` executed verbatim vs train.collate on the same two scenes."""
+    from canonicalvoting_b200 import train
+    g = np.load(os.path.join(GOLD, "refpy_collate.npz"))
+    coords, feats, xyz, scale, cls = train.collate([synthetic.make_scene(300, 16, 4, seed=s) for s in (0, 1)])
+    assert coords.dtype == torch.int32 and cls.dtype == torch.int64
+    for got, key in ((coords, "coords"), (feats, "feats"), (xyz, "xyz"), (scale, "scale"), (cls, "cls")):
+        np.testing.assert_array_equal(got.numpy(), g[key])

@@ -17,6 +17,7 @@ repository except the resulting numbers.
     train_joint.py:253-282          joint loss of the training step (xyz_component_weights 1,1,1; factors of config.yaml)
                                                                                           -> tests/golden/refpy_loss.npz
     train_joint.py:128-133,200-206,224  learning-rate and BN-momentum schedules           -> tests/golden/refpy_schedules.npz
+    train_joint.py:78-90            collate_fn (ME.utils.batched_coordinates = this repository's)  -> tests/golden/refpy_collate.npz
     utils/minkunet.py:122-180       MinkUNetBase.forward, the wiring of the U-Net: the reference class (imported unmodified on the
                                     MinkowskiEngine/ compat package) runs on CPU with the sparse ops routed to the convolution oracle
                                                                                           -> tests/golden/refpy_unet_wiring.npz
@@ -247,6 +248,16 @@ def main():
     np.savez_compressed(os.path.join(OUT, "refpy_schedules.npz"), epochs=epochs, lr=np.array([senv["get_current_lr"](int(e)) for e in epochs]),
                         bn=np.array([senv["bn_lbmd"](int(e)) for e in epochs]))
     print("schedules", senv["get_current_lr"](130), senv["bn_lbmd"](45))
+
+    # ---- collate_fn of train_joint.py (:78-90) on two synthetic scenes
+    import MinkowskiEngine as ME_compat
+    cenv = {"torch": torch, "np": np, "ME": ME_compat}
+    exec(re.search(r"^def collate_fn\(.*?(?=^\S)", tj, re.M | re.S).group(0), cenv)
+    scenes = [synthetic.make_scene(300, 16, 4, seed=s_) for s_ in (0, 1)]
+    batch = [("id%d" % i, torch.from_numpy(s_["coords"]), s_["feats"], s_["xyz_labels"], s_["scale_labels"], s_["class_labels"]) for i, s_ in enumerate(scenes)]
+    _, cb, fb, xb, sb, lb = cenv["collate_fn"](batch)
+    np.savez_compressed(os.path.join(OUT, "refpy_collate.npz"), coords=cb.numpy(), feats=fb.numpy(), xyz=xb.numpy(), scale=sb.numpy(), cls=lb.numpy())
+    print("collate", tuple(cb.shape), cb.dtype)
 
     # ---- U-Net wiring: the reference's MinkUNetBase.forward on CPU
     unet_wiring_golden()
