@@ -43,3 +43,44 @@ def test_iou_and_nms_follow_the_reference_rules():
     assert O.nms(boxes, scores, 0.34) == [0, 3, 2]
     classes = np.array([1, 0, 1, 0])
     assert O.nms_per_class(boxes, scores, classes, 3, 0.3) == [3, 0, 2]
+
+
+def test_intersection_area_against_qhull():
+    """The oracle's Sutherland-Hodgman clipping against an independent construction of the same area (scipy / Qhull: the
+    intersection of the 8 half-planes of two rectangles, Chebyshev centre by linear programming) on random oriented boxes --
+    the stand-in for the shapely polygons of utils/calc_map.py:15-19, which cannot be installed here."""
+    from scipy.optimize import linprog
+    from scipy.spatial import ConvexHull, HalfspaceIntersection
+
+    def halfplanes(q):                        # rows [a, b, c]: a x + b y + c <= 0 inside, for a quad in either orientation
+        c0 = q.mean(0)
+        rows = []
+        for i in range(4):
+            p, r = q[i], q[(i + 1) % 4]
+            nrm = np.array([r[1] - p[1], -(r[0] - p[0])])
+            nrm /= np.linalg.norm(nrm)
+            off = -nrm @ p
+            if nrm @ c0 + off > 0:
+                nrm, off = -nrm, -off
+            rows.append([nrm[0], nrm[1], off])
+        return np.array(rows)
+
+    def qhull_area(q1, q2):
+        H = np.vstack([halfplanes(q1), halfplanes(q2)])
+        # Chebyshev centre: maximise r subject to a.x + r <= -c
+        res = linprog([0, 0, -1], A_ub=np.hstack([H[:, :2], np.ones((8, 1))]), b_ub=-H[:, 2], bounds=[(None, None), (None, None), (0, None)])
+        if not res.success or res.x[2] < 1e-9:
+            return 0.0
+        return ConvexHull(HalfspaceIntersection(H, res.x[:2]).intersections).volume
+
+    rng = np.random.default_rng(3)
+    checked = overlapping = 0
+    for _ in range(300):
+        b1 = _box(rng.uniform(0, 2), rng.uniform(0, 2), rng.uniform(0.2, 1.5), rng.uniform(0.2, 1.5), rng.uniform(0, 2 * np.pi))
+        b2 = _box(rng.uniform(0, 2), rng.uniform(0, 2), rng.uniform(0.2, 1.5), rng.uniform(0.2, 1.5), rng.uniform(0, 2 * np.pi))
+        q1, q2 = b1[:4][:, [0, 2]].astype(float), b2[:4][:, [0, 2]].astype(float)
+        got, want = O.quad_intersection_area(q1, q2), qhull_area(q1, q2)
+        assert abs(got - want) <= 1e-9 + 1e-9 * want, (got, want)
+        checked += 1
+        overlapping += want > 1e-6
+    assert checked == 300 and overlapping > 100
