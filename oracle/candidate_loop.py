@@ -9,9 +9,11 @@ Two restatements of the same lines:
 
   loop_torch()   the script's own torch op sequence on CPU tensors (argmax / slicing / matmul /
                  boolean-mask indexing / unique), i.e. what the reference executes, minus the
-                 `.cuda()` calls.  The reference has no test or golden vector for this loop, so
-                 this function IS the pin: the numpy restatement below and the CUDA kernel are
-                 both checked against it.
+                 `.cuda()` calls.  The reference has no test or golden vector for this loop; both
+                 restatements are pinned by golden vectors obtained from the reference script itself
+                 (tools/make_ref_python_golden.py executes eval_joint.py:196-268 and
+                 eval_separate.py:203-260 verbatim on CPU tensors -> tests/golden/refpy_loop_*.npz,
+                 checked by tests/test_oracle_refpy.py), and the CUDA kernel is checked against them.
   loop_numpy()   float32 numpy with every arithmetic step spelled out in the order the CUDA
                  kernel uses (no library matmul, no FMA), so that integer decisions (which voxels
                  are zeroed, which points are inside, class ids) can be compared bit-exactly.

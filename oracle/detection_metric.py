@@ -5,7 +5,8 @@ precision / recall curve, VOC-07 11-point or area under the precision envelope),
 detections of one class to ground-truth boxes, one match per box) and :177-226 (grouping by class; without the process pool,
 results keyed by class), and the summary dictionary of eval_joint.py:92-110.  Written as plain loops over explicit records,
 IoUs one pair at a time from oracle/obb_nms.get_iou_obb (float64 polygon clipping; shapely is absent here).  The reference
-holds no golden vectors for this code: pinned by hand-computed cases (tests/test_oracle_map.py), parity unpinned beyond those.
+holds no golden vectors for this code: pinned by hand-computed cases (tests/test_oracle_map.py) and by golden vectors from the
+reference functions `voc_ap` / `eval_det_cls` executed verbatim with the same IoU injected (tests/golden/refpy_metric.npz).
 """
 import numpy as np
 

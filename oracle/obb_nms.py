@@ -5,7 +5,9 @@ CPU restatement of the detection post-process that follows the candidate loop: t
 The reference computes the xz-rectangle intersection with shapely (GEOS), which is NOT installed here and not
 vendored: **parity unpinned** against shapely itself.  The polygon intersection is restated as Sutherland-Hodgman
 clipping of convex quadrilaterals in float64 and pinned by analytic cases (tests/test_oracle_nms.py: axis-aligned
-overlaps, a 45-degree rotated square, containment, disjoint and touching boxes)."""
+overlaps, a 45-degree rotated square, containment, disjoint and touching boxes) and by an independent construction of the
+same area with scipy / Qhull on random rectangle pairs; `nms` / `nms_per_class` are pinned by the pick lists of the
+reference's own `nms` function executed verbatim (tests/golden/refpy_nms.npz, tests/test_oracle_refpy.py)."""
 import numpy as np
 
 

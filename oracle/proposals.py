@@ -4,8 +4,10 @@ CPU restatement of the vote-map proposal sampler, sunrgbd/brnetcanon.py:104-162 
 vote): `sample_torch` is the script's own torch op sequence on CPU tensors with the random draw injected (`draws`: the
 int64 cell indices torch.multinomial would return, one tensor per trial); `sample_numpy` is an explicit float32
 restatement with the distance written out ((a-b)^2 summed, then sqrt) instead of torch.cdist.  The two agree exactly
-away from the 0.3 m rejection boundary (tests/test_oracle_proposals.py).  No reference test or golden vector exists
-for this module, and mmdet3d/BRNet (its caller) is absent: parity unpinned beyond the lifted op sequence.
+away from the 0.3 m rejection boundary (tests/test_oracle_proposals.py).  No reference test exists for this module and
+mmdet3d/BRNet (its caller) is absent; both functions are pinned by golden vectors from the reference module itself
+(tools/make_ref_python_golden.py executes sunrgbd/brnetcanon.py:119-161 verbatim with recorded multinomial draws ->
+tests/golden/refpy_proposals.npz, tests/test_oracle_refpy.py).
 """
 import numpy as np
 import torch
