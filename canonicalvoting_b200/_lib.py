@@ -34,7 +34,7 @@ SIGNATURES = {
                                             _f, _i32, ctypes.c_float, _i32, _f, _f, _vp, _vp, ctypes.c_size_t, _vp]),
 }
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 class BpParams(ctypes.Structure):
@@ -70,6 +70,7 @@ SIGNATURES.update({
     "cvb200_sc_set_conv_debug": (ctypes.c_int, [_i32]),
     "cvb200_sc_set_conv_trace": (ctypes.c_int, [_vp]),
     "cvb200_sc_conv_forward_bf16": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64, _i32, _f, _vp, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "cvb200_sc_conv_bf16_chunk": (ctypes.c_int, [_i32, _i32, _i32, _i32, ctypes.POINTER(_i32)]),
     "cvb200_sc_conv_plan_bf16": (ctypes.c_int, [_i64, _i32, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32), _i32]),
     "cvb200_sc_conv_plan": (ctypes.c_int, [_i64, _i32, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32), _i32]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),

@@ -75,6 +75,23 @@ __host__ __device__ __forceinline__ BfUnit bf_unit(const BfPlan &P, int u) {
     return U;
 }
 
+// Where chunk c (16 bytes = 8 channels) of k-block `it` comes from on the flattened (offset, channel) axis.  k_lo / single are
+// warp-uniform (they depend on `it` only): the k-block touches offsets k_lo and, unless `single`, k_lo + 1.
+struct BfChunk {
+    int k_lo, single, valid, use_hi, ch;
+};
+__host__ __device__ __forceinline__ BfChunk bf_chunk(int it, int c, int cin, int ktot) {
+    BfChunk r;
+    r.k_lo = (it * kBfKB) / cin;
+    r.single = (it * kBfKB + kBfKB - 1) / cin == r.k_lo;
+    const int flat = it * kBfKB + 8 * c;
+    const int k_mine = flat / cin;
+    r.valid = flat < ktot;
+    r.use_hi = k_mine != r.k_lo;
+    r.ch = flat - k_mine * cin;
+    return r;
+}
+
 __device__ __forceinline__ void bf_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -227,7 +244,6 @@ sc_conv_bf16_kernel(const __grid_constant__ CUtensorMap map_b, const __nv_bfloat
             for (; it < U.kb1; it += W) {
 #pragma unroll
                 for (int m = 0; m < 4; m++) { lo[m] = nlo[m]; hi[m] = nhi[m]; }
-                const int k_lo = (it * kBfKB) / cin;
                 if (it + W < U.kb1) {       // ids of my next k-block: in flight while this one is copied
                     const int kn = ((it + W) * kBfKB) / cin;
 #pragma unroll
@@ -236,11 +252,10 @@ sc_conv_bf16_kernel(const __grid_constant__ CUtensorMap map_b, const __nv_bfloat
                         nhi[m] = (32 * m < lane_rows && kn + 1 < k3) ? __ldg(nlane + (size_t)(32 * m) * k3 + kn + 1) : -1;
                     }
                 }
-                const int flat = it * kBfKB + 8 * c;                       // my chunk on the flattened (offset, channel) axis
-                const bool valid = flat < ktot;
-                const int k_mine = flat / cin, ch = flat - k_mine * cin;
-                const bool use_hi = k_mine != k_lo;
-                const bool single = (it * kBfKB + kBfKB - 1) / cin == k_lo;   // warp-uniform: the k-block lies inside one offset
+                const BfChunk mine = bf_chunk(it, c, cin, ktot);            // my chunk on the flattened (offset, channel) axis
+                const bool valid = mine.valid != 0, use_hi = mine.use_hi != 0;
+                const bool single = mine.single != 0;                       // warp-uniform: the k-block lies inside one offset
+                const int ch = mine.ch;
                 const int n = n_base + it - U.kb0;
                 const int round = n / P.stages, s = n - round * P.stages;
                 if (!dep_done) {
@@ -555,6 +570,14 @@ extern "C" int cvb200_sc_conv_forward_bf16(const void *d_in, int64_t n_in, int32
     CVB_CUDA(cudaLaunchKernelEx(&cfg, sc_conv_bf16_kernel, map_b, (const __nv_bfloat16 *)d_in, (int)ldi, (int)cin, (const int *)d_nbr,
                                 (int)n_out, (int)k3, d_bias, (const __nv_bfloat16 *)d_res, (int)ldr, (int)relu, d_out, (int)ldo, (int)out_f32, P,
                                 ws.scratch, ws.counters));
+    return 0;
+}
+
+/* Host-only test hook: the gather warp's index arithmetic (bf_chunk) for k-block `it`, chunk c: out[5] = {k_lo, single, valid, use_hi, ch}. */
+extern "C" int cvb200_sc_conv_bf16_chunk(int32_t it, int32_t c, int32_t cin, int32_t k3, int32_t *out) {
+    CVB_REQUIRE(out && it >= 0 && c >= 0 && c < 8 && cin >= 32 && cin % 32 == 0 && k3 > 0, CVB200_EINVAL, "sc_conv_bf16_chunk: bad argument");
+    const BfChunk r = bf_chunk(it, c, cin, k3 * cin);
+    out[0] = r.k_lo; out[1] = r.single; out[2] = r.valid; out[3] = r.use_hi; out[4] = r.ch;
     return 0;
 }
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 12
+#define CVB200_ABI_VERSION 13
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -241,6 +241,9 @@ int cvb200_sc_conv_plan(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, in
 int cvb200_sc_conv_forward_bf16(const void *d_in, int64_t n_in, int32_t ldi, int32_t cin, const void *d_w, int32_t cout,
                                 const int32_t *d_nbr, int64_t n_out, int32_t k3, const float *d_bias, const void *d_res, int32_t ldr,
                                 int32_t relu, void *d_out, int32_t ldo, int32_t out_f32, void *stream);
+/* Host-only test hook: the index arithmetic of its gather warps for k-block `it`, chunk c (0..7): out[5] = {k_lo, single, valid,
+ * use_hi, ch} -- the chunk holds channels ch..ch+7 of kernel offset k_lo + use_hi; `single`: the k-block lies inside one offset. */
+int cvb200_sc_conv_bf16_chunk(int32_t it, int32_t c, int32_t cin, int32_t k3, int32_t *out);
 /* Host-only: its work plan, same layout as cvb200_sc_conv_plan (total_kb counts k-blocks of 64 elements of the flattened axis). */
 int cvb200_sc_conv_plan_bf16(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units, int32_t max_units);
 

@@ -87,3 +87,21 @@ def test_bf16_plan_covers_every_k_block_once(lib_built, n_out, cin, cout, k3):
         assert kb1 > kb0
         cover[row0 // 128, n0 // nc, kb0:kb1] += 1
     assert (cover == 1).all()
+
+
+@pytest.mark.parametrize("cin,k3", [(32, 27), (96, 27), (128, 27), (64, 8), (160, 1), (96, 125), (32, 1)])
+def test_kernel_index_arithmetic_equals_the_emulation(lib_built, cin, k3):
+    """bf_chunk -- the function the CUDA gather warps call -- evaluated on the host for every (k-block, chunk) against the python
+    formulation the emulation above uses."""
+    from canonicalvoting_b200 import _lib
+    L = _lib.load()
+    ktot = k3 * cin
+    out = (ctypes.c_int32 * 5)()
+    for it in range(-(-ktot // B.KB)):
+        k_lo = (B.KB * it) // cin
+        single = (B.KB * it + B.KB - 1) // cin == k_lo
+        for c in range(8):
+            assert L.cvb200_sc_conv_bf16_chunk(it, c, cin, k3, out) == 0
+            k_mine, ch = B.chunk_source(it, c, cin)
+            assert list(out) == [k_lo, int(single), int(B.KB * it + 8 * c < ktot), int(k_mine != k_lo), ch]
+            assert out[2] == 0 or k_mine < k3
