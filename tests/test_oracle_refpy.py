@@ -196,3 +196,17 @@ def test_collate_matches_the_reference_function():
     assert coords.dtype == torch.int32 and cls.dtype == torch.int64
     for got, key in ((coords, "coords"), (feats, "feats"), (xyz, "xyz"), (scale, "scale"), (cls, "cls")):
         np.testing.assert_array_equal(got.numpy(), g[key])
+
+
+def test_scene_detection_tuples_match_the_reference_script():
+    """eval_joint.py:265-281 executed verbatim (arrays -> per-class nms -> (category, box, prob) tuples, with the script's
+    idx2name / name2catname tables) vs oracle nms_per_class + evaluate.scene_detections and evaluate.CATEGORIES."""
+    from canonicalvoting_b200 import evaluate as E
+    g = np.load(os.path.join(GOLD, "refpy_scene_tuples.npz"))
+    assert tuple(g["categories"]) == E.CATEGORIES
+    keep = np.asarray(ON.nms_per_class(g["boxes"], g["scores"], g["classes"], 9, 0.3), dtype=np.int64)
+    dets = E.scene_detections(g["boxes"], g["scores"], g["classes"], keep)
+    assert 0 < len(dets) < len(g["boxes"])
+    assert [d[0] for d in dets] == list(g["names"])
+    np.testing.assert_array_equal(np.stack([d[1] for d in dets]), g["out_boxes"])
+    np.testing.assert_array_equal(np.array([d[2] for d in dets]), g["out_probs"])

@@ -12,6 +12,8 @@ repository except the resulting numbers.
     eval_joint.py:196-268   candidate loop (+ :19-22 thresholds, :60-66 unravel_index)   -> tests/golden/refpy_loop_*.npz
     eval_separate.py:203-260 the per-category variant of the loop (zeroes [c-2, c+2), threshold 60 hard-coded, no class vote)
                                                               -> tests/golden/refpy_loop_sep.npz
+    eval_joint.py:265-281   detection tuples of a scene (arrays, per-class nms, idx2name / name2catname :113-135)
+                                                              -> tests/golden/refpy_scene_tuples.npz
     eval_joint.py:75-89     nms  (IoU injected: oracle/obb_nms.get_iou_obb, shapely is absent)
     utils/calc_map.py:40-71,78-168  voc_ap, eval_det_cls (IoU injected likewise)          -> tests/golden/refpy_metric.npz
     train_joint.py:253-282          joint loss of the training step (xyz_component_weights 1,1,1; factors of config.yaml)
@@ -191,6 +193,30 @@ def main():
     np.savez_compressed(os.path.join(OUT, "refpy_loop_sep.npz"), grids_sha1=hashlib.sha1(go.tobytes() + gr.tobytes() + gs.tobytes()).hexdigest(),
                         boxes=np.asarray(boxes, np.float32).reshape(-1, 8, 3), scores=np.asarray(scores, np.float64),
                         zeroed=np.flatnonzero(grid_after.numpy().reshape(-1) != go.reshape(-1)).astype(np.int32), **c)
+
+    # ---- detection tuples of a scene: eval_joint.py:265-281 (arrays, per-class nms, category names) on the boxes of loop case b
+    denv = dict(env)
+    ej = open(os.path.join(REF, "eval_joint.py")).read()
+    for name in ("idx2name", "name2catname"):
+        exec(re.search(r"^%s = \{.*?^\}" % name, ej, re.M | re.S).group(0), denv)
+    denv["SCENENN"] = False
+    sc = synthetic.make_scene(12000, 48, 8, seed=5, n_objects=12)
+    go, gr, gs = O.forward(sc["points"], sc["xyz"], sc["scale"], sc["obj"], np.float32(0.03), 8, threads=1)
+    env["thresh_high"] = 60.0 * 8 / 120
+    t = torch.from_numpy
+    boxes, scores, probs, classes, _ = ref_loop(t(go.copy()), t(gr), t(gs), t(sc["coords"].astype(np.int64)), t(sc["xyz"]), t(sc["obj"]), t(sc["class_pred"]))
+    rng = np.random.default_rng(1)                     # duplicate every box with jitter so that the NMS has something to suppress
+    boxes = [b for b in boxes] + [b + rng.normal(0, 0.02, b.shape).astype(np.float32) for b in boxes]
+    scores = list(scores) + [float(s_ - 0.01 * (i + 1)) for i, s_ in enumerate(scores)]
+    probs, classes = list(scores), list(classes) + list(classes)
+    tuples = make_function("ref_scene_tuples", ["boxes", "scores", "probs", "classes"], "map_scene = []\n" + cut("eval_joint.py", 265, 281),
+                           "map_scene", denv)(boxes, scores, probs, classes)
+    cats = sorted(set(denv["name2catname"][denv["idx2name"][i]] for i in range(9)))
+    np.savez_compressed(os.path.join(OUT, "refpy_scene_tuples.npz"), boxes=np.asarray(boxes, np.float32), scores=np.asarray(scores, np.float64),
+                        classes=np.asarray(classes, np.int64), names=np.array([c_ for c_, _, _ in tuples]),
+                        out_boxes=np.asarray([b_ for _, b_, _ in tuples], np.float32), out_probs=np.asarray([p_ for _, _, p_ in tuples], np.float64),
+                        categories=np.array([denv["name2catname"][denv["idx2name"][i]] for i in range(9)]))
+    print("scene tuples", len(tuples), "of", len(boxes))
 
     # ---- head decode: eval_joint.py:173-190 on random network outputs
     decode = make_function("ref_decode", ["scan_output", "scan_points"], cut("eval_joint.py", 173, 190), "xyz_pred, scale_pred, class_pred, prob_pred", env)
