@@ -114,7 +114,7 @@ def test_world_size_2_sharded_evaluation_equals_single_process():
     want = OM.compute_map(pred_all, gt_all, 0.25)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29500 + os.getpid() % 400
+    port = 30100 + os.getpid() % 400          # disjoint from the range tests/test_train_host.py uses
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
