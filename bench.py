@@ -254,8 +254,6 @@ def main():
         from canonicalvoting_b200 import _lib
         o = [int(x) for x in os.environ["CVB200_CONV_OPTS"].split(",")]
         _lib.load().cvb200_sc_set_conv_options(o[0], o[1])
-        if len(o) > 2:
-            _lib.load().cvb200_sc_set_conv_impl(o[2])
         if len(o) > 3:
             _lib.load().cvb200_sc_set_conv_debug(o[3])
     rank = int(os.environ.get("RANK", "0"))

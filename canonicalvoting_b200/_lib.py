@@ -21,6 +21,8 @@ SIGNATURES = {
     "cvb200_hv_grid_dims": (ctypes.c_int, [_f, _i64, ctypes.c_float, _vp, ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32), _vp]),
     "cvb200_hv_forward_work_bytes": (ctypes.c_size_t, [ctypes.POINTER(_i32)]),
+    "cvb200_hv_forward_work_bytes_n": (ctypes.c_size_t, [ctypes.POINTER(_i32), _i64, _i32]),
+    "cvb200_hv_set_impl": (ctypes.c_int, [_i32]),
     "cvb200_hv_forward": (ctypes.c_int, [_f, _f, _f, _f, _i64, ctypes.c_float, _i32, ctypes.POINTER(ctypes.c_float),
                                           ctypes.POINTER(_i32), _f, _f, _f, _vp, ctypes.c_size_t, _vp]),
     "cvb200_hv_backward": (ctypes.c_int, [_f, _f, _f, _f, _f, _i64, ctypes.c_float, _i32,
@@ -34,7 +36,7 @@ SIGNATURES = {
                                             _f, _i32, ctypes.c_float, _i32, _f, _f, _vp, _vp, ctypes.c_size_t, _vp]),
 }
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class BpParams(ctypes.Structure):
@@ -65,13 +67,9 @@ SIGNATURES.update({
     "cvb200_sc_kernel_map": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "cvb200_sc_conv_forward": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
     "cvb200_sc_conv_forward_tc": (ctypes.c_int, [_f, _i64, _i32, _f, _i32, _vp, _i64, _i32, _f, _f, _vp]),
-    "cvb200_sc_set_conv_impl": (ctypes.c_int, [_i32]),
     "cvb200_sc_set_conv_options": (ctypes.c_int, [_i32, _i32]),
     "cvb200_sc_set_conv_debug": (ctypes.c_int, [_i32]),
     "cvb200_sc_set_conv_trace": (ctypes.c_int, [_vp]),
-    "cvb200_sc_conv_forward_bf16": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64, _i32, _f, _vp, _i32, _i32, _vp, _i32, _i32, _vp]),
-    "cvb200_sc_conv_bf16_chunk": (ctypes.c_int, [_i32, _i32, _i32, _i32, ctypes.POINTER(_i32)]),
-    "cvb200_sc_conv_plan_bf16": (ctypes.c_int, [_i64, _i32, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32), _i32]),
     "cvb200_sc_conv_plan": (ctypes.c_int, [_i64, _i32, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32), _i32]),
     "cvb200_sc_conv_wgrad": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _i32, _f, _vp]),
     "cvb200_sc_conv_wgrad_tc": (ctypes.c_int, [_f, _i32, _f, _i32, _vp, _i64, _i32, _f, _vp]),
@@ -83,7 +81,7 @@ class ScOp(ctypes.Structure):
     """cvb200_sc_op (include/cvb200.h)."""
     _fields_ = [("kind", _i32), ("cin", _i32), ("cout", _i32), ("k3", _i32), ("ldi", _i32), ("ldo", _i32), ("ldr", _i32),
                 ("relu", _i32), ("n_out", _i64), ("n_in", _i64), ("in_", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("table", _vp),
-                ("out", _vp)]
+                ("out", _vp), ("n_out_dev", _vp)]
 
 
 class MapsLayout(ctypes.Structure):

@@ -35,6 +35,16 @@
 
 namespace cvb200 {
 
+// The measurement aids (cvb200_sc_set_conv_debug masks, clock64 traces; tools/conv_probe.py, tools/conv_trace.py) exist only in a
+// probe build (CVB200_PROBE=1 python -m canonicalvoting_b200.build --force): the shipped kernel carries none of their branches.
+#ifdef CVB200_PROBE
+#define PS_DBG(P, mask) (((P).dbg & (mask)) != 0)
+#define PS_TRACE(trace) ((trace) != nullptr && blockIdx.x == 0)
+#else
+#define PS_DBG(P, mask) false
+#define PS_TRACE(trace) false
+#endif
+
 constexpr int kPsM = 128, kPsKB = 32, kPsThreads = 416, kPsMaxStages = 8;
 constexpr int kPsProducers = 4;   // gather warps 1,2,3,5 (6,7 too when set to 6: measured slower); TMA warp 0; MMA issuers 4 and 12 (same
                                   // scheduler as warp 0); epilogue warps 8..11
@@ -42,11 +52,6 @@ constexpr int kPsSmemBytes = 224 * 1024;                   // of the 227 KiB a C
 constexpr int kPsMaxSplitTiles = 2 * kNumSMs;                   // tiles that can be split in one launch (one partial wave)
 constexpr size_t kPsScratchFloats = (size_t)kPsMaxSplitTiles * kPsM * 128;
 
-struct PsHeader {
-    unsigned long long full_bar[kPsMaxStages], empty_bar[kPsMaxStages], acc_full[2], acc_empty[2], turn[2];
-    unsigned int tmem_base;
-    int last_flag;
-};
 
 struct PsPlan {
     int n_tiles;      // row tiles x channel splits
@@ -61,7 +66,46 @@ struct PsPlan {
     int acc_stride;   // TMEM column offset of the second accumulator
     int tmem_cols;
     int dbg;          // measurement aid (cvb200_sc_set_conv_debug): 1 no gather copies, 2 no zero-fill copies, 4 no MMA, 8 no weight TMA
+    int allow_split;  // 0: never cut tiles into pieces
+    int force_ks;     // probe override of ks (0 = planner's choice)
 };
+
+struct PsHeader {
+    unsigned long long full_bar[kPsMaxStages], empty_bar[kPsMaxStages], acc_full[2], acc_empty[2], turn[2];
+    unsigned int tmem_base;
+    int last_flag;
+    int n_out;        // rows of this launch (read from device memory when the launch is size-agnostic)
+    PsPlan plan;      // the plan for n_out rows
+};
+
+// The row-dependent half of the plan: how the n_out rows are cut into units for `slots` persistent CTAs.  Host and device:
+// a size-agnostic launch (row count in device memory, e.g. inside a CUDA graph) plans in the kernel.
+__host__ __device__ inline void ps_plan_rows(long long n_out, int slots, PsPlan *P) {
+    const int m_tiles = (int)((n_out + kPsM - 1) / kPsM);
+    P->n_tiles = m_tiles * P->n_splits;
+    const int S = slots;
+    P->n_whole = (P->n_tiles / S) * S;
+    const int R = P->n_tiles - P->n_whole;
+    int best_ks = 1;
+    if (R > 0 && P->allow_split) {
+        // rounds of the partial wave x (k-blocks per piece + fixed cost of a unit) + cost of the split epilogue, in k-block units
+        double best = 1e30;
+        for (int ks = 1; ks <= 32 && ks <= P->total_kb; ks++) {
+            const int rounds = (int)(((long long)R * ks + S - 1) / S);
+            const int per = (P->total_kb + ks - 1) / ks;
+            const double cost = rounds * (per + 6.0) + (ks > 1 ? 8.0 : 0.0);
+            if (cost < best - 1e-9) { best = cost; best_ks = ks; }
+        }
+    }
+    if (P->force_ks > 0 && R > 0) best_ks = P->force_ks < P->total_kb ? P->force_ks : P->total_kb;   // probe override
+    P->ks = best_ks;
+    if (best_ks == 1) P->n_whole = P->n_tiles;
+    if (P->n_tiles - P->n_whole > 2 * kNumSMs) {   // cannot happen with S <= 2 * kNumSMs and the scratch sized for it; be safe
+        P->ks = 1;
+        P->n_whole = P->n_tiles;
+    }
+    P->n_units = P->n_whole + (P->n_tiles - P->n_whole) * P->ks;
+}
 
 struct PsUnit {
     int row0, n0, kb0, kb1, pieces, split_tile;
@@ -111,37 +155,53 @@ __device__ __forceinline__ void ps_cp_async_wait(int n) {
 __global__ void __launch_bounds__(kPsThreads, 1)
 sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *__restrict__ in, int ldi, int cout_total,
                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
-                       const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P,
-                       float *__restrict__ scratch, int *__restrict__ counters, long long *__restrict__ trace, int g4) {
+                       const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P0,
+                       float *__restrict__ scratch, int *__restrict__ counters, long long *__restrict__ trace, int g4,
+                       const int *__restrict__ n_out_dev) {
     extern __shared__ __align__(1024) unsigned char smem[];
     PsHeader &H = *reinterpret_cast<PsHeader *>(smem);
     unsigned char *stage0 = smem + 1024 + 16384;       // [header 1 KiB][epilogue staging 4 x 4 KiB][ring]
-    const int a_bytes = kPsM * 128, b_bytes = P.nc * 128, stage_bytes = a_bytes + b_bytes;
+    const int a_bytes = kPsM * 128, b_bytes = P0.nc * 128, stage_bytes = a_bytes + b_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool tr = trace != nullptr && blockIdx.x == 0;   // measurement aid: clock64 stamps of the first 256 k-blocks of CTA 0
+    const bool tr = PS_TRACE(trace);   // measurement aid: clock64 stamps of the first 256 k-blocks of CTA 0
     int tn = 0;
     if (tr && tid == 0) trace[3 * 768 + 0] = clock64();
 
     if (tid == 0) {
-        for (int s = 0; s < P.stages; s++) {
+        for (int s = 0; s < P0.stages; s++) {
             tm_mbar_init(tm_smem_u32(&H.full_bar[s]), 1 + 32);
             tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
-            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), (P.dbg & 0x40000) ? 1 : 2);      // both MMA warps
+            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), PS_DBG(P0, 0x40000) ? 1 : 2);      // both MMA warps
             tm_mbar_init(tm_smem_u32(&H.acc_empty[b]), 4);
             tm_mbar_init(tm_smem_u32(&H.turn[b]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid == 32) {
+        // size-agnostic launch: the row count was written by the map builder (complete before the first convolution of the
+        // program starts, like the neighbour tables), n_out is its upper bound; the plan is made here
+        PsPlan Q = P0;
+        int rows = n_out;
+        if (n_out_dev) {
+            const int dev_rows = __ldg(n_out_dev);
+            rows = dev_rows < n_out ? (dev_rows > 0 ? dev_rows : 0) : n_out;
+            ps_plan_rows(rows, (int)gridDim.x, &Q);
+        }
+        H.plan = Q;
+        H.n_out = rows;
+    }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tm_smem_u32(&H.tmem_base)), "r"(P.tmem_cols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tm_smem_u32(&H.tmem_base)), "r"(P0.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = H.tmem_base;
+    const PsPlan P = H.plan;
+    n_out = H.n_out;
     // everything above overlapped the previous kernel of the stream; its results are visible after this wait
     if (tr && tid == 0) trace[3 * 768 + 1] = clock64();
     // Programmatic dependent launch: everything above overlapped the previous kernel of the stream.  Only what depends
@@ -164,7 +224,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 const uint32_t b_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes) + a_bytes;
                 const uint32_t full = tm_smem_u32(&H.full_bar[s]);
                 if (tm_elect_one()) {
-                    if (P.dbg & 8) {
+                    if (PS_DBG(P, 8)) {
                         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
                     } else {
                         tm_expect_tx(full, (uint32_t)b_bytes);
@@ -187,7 +247,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // order, stages are released in order, and the first k-block of a unit overwrites the accumulator before anything
         // is added to it.  Both warps commit to acc_full (count 2).
         const int me = warp == 4 ? 0 : 1;
-        const int issuers = (P.dbg & 0x40000) ? 1 : 2;            // measurement aid: one issuer only (warp 12 idles)
+        const int issuers = PS_DBG(P, 0x40000) ? 1 : 2;            // measurement aid: one issuer only (warp 12 idles)
         int li = 0, n_base = 0;
         for (int u = blockIdx.x; u < P.n_units && me < issuers; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
@@ -207,12 +267,12 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 if (tr && me == 0 && lane == 0 && tn < 256) { trace[3 * tn] = t0; trace[3 * tn + 1] = clock64(); }
                 const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
                 const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
-                if (!(P.dbg & 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
+                if (!PS_DBG(P, 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
                 // my turn: the other warp has issued k-block n - 1
                 if (n > 0 && issuers == 2) tm_mbar_wait(tm_smem_u32(&H.turn[me]), (uint32_t)(((n >> 1) + me + 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tm_elect_one()) {
-                    if (!(P.dbg & 4)) {
+                    if (!PS_DBG(P, 4)) {
 #pragma unroll
                         for (int kk = 0; kk < kPsKB / 8; kk++)
                             tm_umma_tf32(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (it > U.kb0 || kk > 0) ? 1u : 0u);
@@ -309,7 +369,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                     const int id = __shfl_sync(0xffffffffu, cur[j >> 3], rb + 4 * (j & 7));   // row rb + 4 j = 32 (j >> 3) + rb + 4 (j & 7)
                     const float *src = src0 + (size_t)(id >= 0 ? id : 0) * ld4;
                     const uint32_t dst = a_s + ((j & 1) ? off_odd : off_even) + (uint32_t)((j >> 1) * 1024);
-                    if (!(P.dbg & 1))
+                    if (!PS_DBG(P, 1))
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(id >= 0 ? 16u : 0u) : "memory");
                 }
                 }
@@ -330,7 +390,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
             const int buf = li & 1;
             // one polling lane per warp: 128 threads parked in try_wait on the header slowed every other mbarrier operation
             // of the CTA down (tools/conv_trace.py)
-            if (lane == 0 || (P.dbg & 128)) tm_mbar_wait(tm_smem_u32(&H.acc_full[buf]), (uint32_t)((li >> 1) & 1));
+            if (lane == 0 || PS_DBG(P, 128)) tm_mbar_wait(tm_smem_u32(&H.acc_full[buf]), (uint32_t)((li >> 1) & 1));
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tr && et == 0 && li == 0) trace[3 * 768 + 3] = clock64();
@@ -379,7 +439,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 for (int ch = 0; ch < P.nc / 32; ch++) {
                     uint32_t v[32];
                     if (!split) {
-                        if (P.dbg & 0x20000) {
+                        if (PS_DBG(P, 0x20000)) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) v[j] = 0u;
                         } else {
@@ -404,7 +464,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                     }
                     const int col = U.n0 + ch * 32 + g * 4;
                     float4 rv[8];
-                    if (residual && !(P.dbg & 0x10000)) {
+                    if (residual && !PS_DBG(P, 0x10000)) {
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const int rr = U.row0 + q * 32 + 4 * i + sub;
@@ -426,9 +486,9 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                                      : "r"(st + (uint32_t)(row * 128 + ((g ^ (row & 7)) << 4))) : "memory");
                         o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        if (residual && !(P.dbg & 0x10000)) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
+                        if (residual && !PS_DBG(P, 0x10000)) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
                         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        if (rr < n_out && !(P.dbg & 0x10000)) *reinterpret_cast<float4 *>(out + (size_t)rr * ldo + col) = o;
+                        if (rr < n_out && !PS_DBG(P, 0x10000)) *reinterpret_cast<float4 *>(out + (size_t)rr * ldo + col) = o;
                     }
                 }
                 if (!split) {
@@ -526,44 +586,21 @@ static int ps_workspace(cudaStream_t stream, PsWorkspace *ws) {
 
 
 static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ctas_per_sm) {
-    const int m_tiles = (int)ceil_div(n_out, kPsM);
     int n_splits = 1;
     while (cout / n_splits > 128 || cout % n_splits != 0 || (cout / n_splits) % 16 != 0) n_splits++;
     P->n_splits = n_splits;
     P->nc = cout / n_splits;
-    P->n_tiles = m_tiles * n_splits;
     P->cblocks = cin / kPsKB;
     P->total_kb = k3 * P->cblocks;
     const int stage_bytes = kPsM * 128 + P->nc * 128;
-    const int dual_bytes = 1024 + 16384 + 3 * stage_bytes;
     // two CTAs per SM with 3-stage rings were measured slower than one deep ring on every level (113 vs 91 us on the large
     // layers) and are no longer offered; the register budget is now spent on one CTA
-    (void)dual_bytes;
     *ctas_per_sm = 1;
-    const int S = kNumSMs * *ctas_per_sm;
-    P->n_whole = (P->n_tiles / S) * S;
-    const int R = P->n_tiles - P->n_whole;
-    int best_ks = 1;
-    if (R > 0 && g_ps_allow_split) {
-        // rounds of the partial wave x (k-blocks per piece + fixed cost of a unit) + cost of the split epilogue, in k-block units
-        double best = 1e30;
-        for (int ks = 1; ks <= 32 && ks <= P->total_kb; ks++) {
-            const int rounds = (int)ceil_div((int64_t)R * ks, S);
-            const int per = (int)ceil_div(P->total_kb, ks);
-            const double cost = rounds * (per + 6.0) + (ks > 1 ? 8.0 : 0.0);
-            if (cost < best - 1e-9) { best = cost; best_ks = ks; }
-        }
-    }
-    if (((g_ps_debug >> 8) & 255) > 0 && R > 0) best_ks = ((g_ps_debug >> 8) & 255) < P->total_kb ? ((g_ps_debug >> 8) & 255) : P->total_kb;   // probe override
-    P->ks = best_ks;
-    if (best_ks == 1) P->n_whole = P->n_tiles;
-    if (P->n_tiles - P->n_whole > kPsMaxSplitTiles) {   // cannot happen with S <= 2 * kNumSMs and the scratch sized for it; be safe
-        P->ks = 1;
-        P->n_whole = P->n_tiles;
-    }
-    P->n_units = P->n_whole + (P->n_tiles - P->n_whole) * P->ks;
+    P->allow_split = g_ps_allow_split;
+    P->force_ks = (g_ps_debug >> 8) & 255;
+    ps_plan_rows(n_out, kNumSMs * *ctas_per_sm, P);
     int stages = (kPsSmemBytes - 1024 - 16384) / stage_bytes;
-    P->stages = *ctas_per_sm == 2 ? 3 : (stages > kPsMaxStages ? kPsMaxStages : stages);
+    P->stages = stages > kPsMaxStages ? kPsMaxStages : stages;
     int cols = 32;
     while (cols < 2 * P->nc) cols <<= 1;
     P->tmem_cols = cols;
@@ -575,7 +612,7 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ct
 // K = 32 * ceil(g4 / 8) = (neighbour, channel) pairs; cin must be that K, k3 must be 1, d_wt = [cout][K]
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
-                        cudaStream_t stream, int g4) {
+                        cudaStream_t stream, int g4, const int32_t *d_n_out) {
     CVB_REQUIRE(g4 == 0 || (k3 == 1 && ldi == 4 && cin == 32 * ((g4 + 7) / 8)), CVB200_EINVAL,
                 "sc_conv (4-channel gather): needs k3 == 1, ldi == 4, cin == 32 * ceil(width / 8) (got %d, %d, %d for width %d)", k3, ldi, cin, g4);
     CVB_REQUIRE(cin > 0 && cin % kPsKB == 0 && cout >= 16 && cout <= 1024 && cout % 16 == 0 && k3 > 0, CVB200_EINVAL,
@@ -601,7 +638,8 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     }
     cudaLaunchConfig_t cfg = {};
     const int slots = kNumSMs * ctas_per_sm;
-    cfg.gridDim = dim3((unsigned)(P.n_units < slots ? P.n_units : slots));
+    // size-agnostic launch (d_n_out: row count in device memory, n_out its upper bound): always the full grid, the kernel plans
+    cfg.gridDim = dim3((unsigned)(d_n_out ? slots : (P.n_units < slots ? P.n_units : slots)));
     cfg.blockDim = dim3(kPsThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -611,11 +649,18 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     cfg.attrs = attr;
     cfg.numAttrs = g_ps_use_pdl ? 1 : 0;
     CVB_CUDA(cudaLaunchKernelEx(&cfg, sc_conv_persist_kernel, map_b, d_in, ldi, cout, (const int *)d_nbr, (int)n_out, k3, d_bias, d_res,
-                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace, g4));
+                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace, g4, (const int *)d_n_out));
     return 0;
 }
 
 }  // namespace cvb200
+
+extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_t cin, const float *d_wt, int32_t cout,
+                                         const int32_t *d_nbr, int64_t n_out, int32_t k3, const float *d_bias, float *d_out,
+                                         void *stream_) {
+    return cvb200::launch_conv_persist(d_in, n_in, cin, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, nullptr, 0, 0, d_out, cout,
+                                       (cudaStream_t)stream_, 0, nullptr);
+}
 
 extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) {
     cvb200::g_ps_allow_split = allow_split != 0;

@@ -11,11 +11,9 @@
 
 namespace cvb200 {
 
-int launch_conv_tc(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr, int64_t n_out,
-                   int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo, cudaStream_t stream);
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
-                        cudaStream_t stream, int g4);
+                        cudaStream_t stream, int g4, const int32_t *d_n_out);
 
 // Convolution with a tiny input width (the 3-channel 5^3 stem, utils/minkunet.py:53): one warp per output row, the
 // whole kernel (K^3 x cin x cout) in shared memory, lanes = output channels; neighbour ids are read 32 at a time and
@@ -121,10 +119,11 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
     for (int i = 0; i < n_ops; i++) {
         const cvb200_sc_op &o = ops[i];
         if (o.kind == CVB200_OP_CONV_TC) {
-            const int rc = launch_conv_tc(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr, o.relu,
-                                          o.out, o.ldo, stream);
+            const int rc = launch_conv_persist(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr,
+                                               o.relu, o.out, o.ldo, stream, 0, o.n_out_dev);
             if (rc) return rc;
         } else if (o.kind == CVB200_OP_CONV_SMALLCIN) {
+            CVB_REQUIRE(!o.n_out_dev, CVB200_EINVAL, "sc_run_program: op %d: a device-side row count needs a tensor-core kind", i);
             CVB_REQUIRE(o.cin >= 1 && o.cin <= 8 && o.cout % 32 == 0 && o.cout <= 128 && !o.residual, CVB200_EINVAL,
                         "sc_run_program: op %d: small-cin convolution needs cin <= 8, cout in {32,64,96,128}, no residual", i);
             const size_t smem = sizeof(float) * (size_t)o.k3 * o.cin * o.cout;
@@ -143,9 +142,10 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
         } else if (o.kind == CVB200_OP_CONV_TC_GATHER4) {
             // 4-channel input gathered 8 neighbours per k-block: o.k3 = table width, o.cin = 32 * ceil(k3 / 8) = K of the weights
             const int rc = launch_conv_persist(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, 1, o.bias, o.residual, o.ldr, o.relu,
-                                               o.out, o.ldo, stream, o.k3);
+                                               o.out, o.ldo, stream, o.k3, o.n_out_dev);
             if (rc) return rc;
         } else if (o.kind == CVB200_OP_IM2COL) {
+            CVB_REQUIRE(!o.n_out_dev, CVB200_EINVAL, "sc_run_program: op %d: a device-side row count needs a tensor-core kind", i);
             CVB_REQUIRE(o.cin >= 1 && o.cin <= 8 && o.ldo % o.cin == 0 && o.ldo >= o.k3 * o.cin && o.in && o.out && o.table, CVB200_EINVAL,
                         "sc_run_program: op %d: im2col needs cin <= 8 and ldo a multiple of cin covering K^3*cin", i);
             if (o.n_out > 0) {

@@ -142,7 +142,7 @@ __device__ __forceinline__ void tm_commit(uint32_t bar) {
 }
 
 // 2-D fp32 tensor map with SWIZZLE_128B, or its 32-byte-atom variant that MN-major tf32 operands need (defined in
-// sparse_conv_tma.cu); returns a cvb200 status
+// tensor_map.cu); returns a cvb200 status
 int make_map_2d(CUtensorMap *m, const float *base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
                 uint32_t box_rows, int swizzle_atom_32b = 0);
 

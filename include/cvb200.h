@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CVB200_ABI_VERSION 13
+#define CVB200_ABI_VERSION 14
 
 #define CVB200_EINVAL   (-1) /* bad argument (null pointer, negative size, ...) */
 #define CVB200_ESCRATCH (-2) /* workspace too small */
@@ -50,12 +50,19 @@ size_t cvb200_hv_grid_dims_work_bytes(void);
 int cvb200_hv_grid_dims(const float *d_points, int64_t n, float res, void *d_work,
                         float *h_corner, float *h_maxpt, int32_t *h_dims, void *stream);
 
-/* Bytes of the device workspace of cvb200_hv_forward for a grid of dims[0..2] voxels:
- * an interleaved accumulator of 8 floats (one 32-byte sector) per voxel.
- * CONTRACT: the workspace must be all-zero when cvb200_hv_forward is entered and is
- * all-zero again when the call's work completes (the write-out pass re-zeroes it), so a caller zero-fills it once after allocation and may
- * then reuse it forever on the same stream.  16-byte alignment required. */
+/* Bytes of the device workspace of cvb200_hv_forward for n points, num_rots rotations and a grid of dims[0..2] voxels:
+ * three uint32 arrays over the 8x8x8-voxel tiles of the grid (counts, offsets, fill cursors) + one 4-byte record per
+ * (vote, touched tile) -- a vote's 2x2x2 footprint touches at most 8 tiles, hence 32 n num_rots bytes of records.
+ * CONTRACT: the tile counters (the first 4 * ceil(X/8) ceil(Y/8) ceil(Z/8) bytes) and the ticket word behind the three arrays
+ * must be zero when cvb200_hv_forward is entered and are zero again when the call's work completes, so a caller
+ * zero-fills the workspace once after allocation and may then reuse it forever on the same stream (also for other grid
+ * sizes only after zero-filling it again).  16-byte alignment required. */
+size_t cvb200_hv_forward_work_bytes_n(const int32_t dims[3], int64_t n, int32_t num_rots);
+
+/* Measurement aid: 0 selects the round-1 forward (vector reductions into an interleaved [G][8] float workspace of
+ * cvb200_hv_forward_work_bytes(dims) bytes + write-out pass), 1 (default) the sorted-tile forward. */
 size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]);
+int cvb200_hv_set_impl(int32_t impl);
 
 /* hv_cuda.forward (houghvoting/src/hv_cuda.cpp:30-45 -> hv_cuda_kernel.cu:121-165):
  * scatter every point's num_rots oriented centre votes into the grid with trilinear
@@ -66,7 +73,7 @@ size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]);
  *   d_grid_obj [X,Y,Z], d_grid_rot [X,Y,Z,2], d_grid_scale [X,Y,Z,3]: outputs, every
  *       element is written exactly once (no pre-zeroing needed; the reference needs 3
  *       memsets)
- *   d_work / work_bytes    see cvb200_hv_forward_work_bytes */
+ *   d_work / work_bytes    see cvb200_hv_forward_work_bytes_n; n * num_rots must be below 2^32 */
 int cvb200_hv_forward(const float *d_points, const float *d_xyz, const float *d_scale, const float *d_obj,
                       int64_t n, float res, int32_t num_rots, const float corner[3], const int32_t dims[3],
                       float *d_grid_obj, float *d_grid_rot, float *d_grid_scale,
@@ -210,20 +217,13 @@ int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_t cin, cons
 int cvb200_sc_conv_wgrad_tc(const float *d_x, int32_t cin, const float *d_dout, int32_t cout, const int32_t *d_table,
                             int64_t n_rows, int32_t k3, float *d_dw, void *stream);
 
-/* Implementation of the tensor-core convolution (all compute the same contraction; selectable for A/B measurements):
- * 3 = persistent warp-specialised kernel: one CTA per SM walks work units, two accumulators in tensor memory, tiles of
- *     the partial wave / of small levels are cut into pieces whose partial sums are combined in-kernel (default);
- * 2 = warp-specialised kernel, one tile per CTA, neighbour rows by cp.async producer warps + weight block by TMA;
- * 1 = same kernel, neighbour rows by TMA tile::gather4;  0 = cp.async kernel with one CTA barrier per k-block. */
-int cvb200_sc_set_conv_impl(int32_t impl);
-
-/* Options of implementation 3.  allow_split = 0: never cut a tile into pieces (no float atomics: bit-reproducible
+/* Options of the tensor-core convolution.  allow_split = 0: never cut a tile into pieces (no float atomics: bit-reproducible
  * results; slower on small levels).  use_pdl = 0: no programmatic dependent launch.  Defaults: 1, 1. */
 int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl);
 
-/* Measurement aid (tools/conv_probe.py): switch off parts of implementation 3 to find which side bounds it -- results are
+/* Measurement aid (tools/conv_probe.py): switch off parts of the kernel to find which side bounds it -- results are
  * garbage while mask != 0.  1 = no gather copies, 2 = no zero-fill copies, 4 = no MMA, 8 = no weight TMA. */
-int cvb200_sc_set_conv_debug(int32_t mask);
+int cvb200_sc_set_conv_debug(int32_t mask);   /* effective only in a probe build (CVB200_PROBE=1 python -m canonicalvoting_b200.build --force) */
 /* Measurement aid: device buffer of 3 x 768 int64 that receives clock64 stamps (before wait, after wait, after issue) of the
  * first 256 k-blocks of CTA 0 for the MMA thread, one gather warp and the weight-TMA thread; NULL switches it off. */
 int cvb200_sc_set_conv_trace(void *d_trace);
@@ -233,19 +233,6 @@ int cvb200_sc_set_conv_trace(void *d_trace);
  * acc_stride, tmem_cols, smem_bytes}; h_units (may be NULL) receives min(n_units, max_units) rows {row0, n0, kb0, kb1, pieces,
  * split_tile}.  Used by the CPU tests to check that every (row tile, channel block, k-block) is covered exactly once. */
 int cvb200_sc_conv_plan(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units, int32_t max_units);
-
-/* EXPERIMENTAL (round-2 work item, not on the product path, not yet run on a GPU): bf16 variant of the persistent tensor-core
- * convolution.  d_in bf16 [n_in, ldi], d_res bf16 [n_out, ldr] (may be NULL), d_out bf16 [n_out, ldo] (float32 when out_f32),
- * d_bias float32 [cout] (may be NULL); d_w bf16 [cout][k3 * cin]: the weights with the contraction axis flattened
- * (w[co][k * cin + c] = kernel[k][c][co]); d_nbr int32 [n_out, k3].  cin % 32 == 0, cout % 16 == 0; strides in elements. */
-int cvb200_sc_conv_forward_bf16(const void *d_in, int64_t n_in, int32_t ldi, int32_t cin, const void *d_w, int32_t cout,
-                                const int32_t *d_nbr, int64_t n_out, int32_t k3, const float *d_bias, const void *d_res, int32_t ldr,
-                                int32_t relu, void *d_out, int32_t ldo, int32_t out_f32, void *stream);
-/* Host-only test hook: the index arithmetic of its gather warps for k-block `it`, chunk c (0..7): out[5] = {k_lo, single, valid,
- * use_hi, ch} -- the chunk holds channels ch..ch+7 of kernel offset k_lo + use_hi; `single`: the k-block lies inside one offset. */
-int cvb200_sc_conv_bf16_chunk(int32_t it, int32_t c, int32_t cin, int32_t k3, int32_t *out);
-/* Host-only: its work plan, same layout as cvb200_sc_conv_plan (total_kb counts k-blocks of 64 elements of the flattened axis). */
-int cvb200_sc_conv_plan_bf16(int64_t n_out, int32_t cin, int32_t cout, int32_t k3, int32_t *h_plan, int32_t *h_units, int32_t max_units);
 
 /* On-device voxelisation = ME.utils.sparse_quantize (utils/dataloader.py:197, sunrgbd/brnetcanon.py:218): d_xyz float32 [n,3];
  * voxel = floor(p / quantization_size) evaluated in float32 (quantization_size <= 0: floor(p)); d_voxel int32 [n,4] receives
@@ -296,6 +283,11 @@ typedef struct cvb200_sc_op {
     const float *residual;   /* [n_out, cout] with row stride ldr, or NULL */
     const int32_t *table;    /* [n_out, k3] neighbour table */
     float *out;
+    const int32_t *n_out_dev; /* NULL, or the address of the real row count in DEVICE memory (written by cvb200_sc_build_maps into the
+                               * counts array of its workspace): n_out is then only an upper bound (the size the buffers have) and the
+                               * kernel plans its work itself -- the launch does not depend on a size the host would have to read
+                               * back, so a whole program can be captured into one CUDA graph and replayed for any scene of that
+                               * bucket.  Tensor-core kinds only. */
 } cvb200_sc_op;
 
 /* Launch the ops of a program in order on `stream` (host array of ops; asynchronous). */

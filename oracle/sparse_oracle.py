@@ -82,6 +82,18 @@ def conv_up(fine_coords, coarse_feats, kernel, tensor_stride=2, bias=None):
     return out + (bias if bias is not None else 0)
 
 
+def conv_table(x, w, table, bias=None):
+    """The one primitive every convolution variant reduces to (canonicalvoting_b200/sparse/functional.py), restated on CPU in
+    float64: out[o] = sum_k x[table[o, k]] @ w[k] (+ bias), a table entry of -1 contributing nothing."""
+    x, w, table = x.detach().cpu().double(), w.detach().cpu().double(), table.detach().cpu().long()
+    out = torch.zeros((table.shape[0], w.shape[2]), dtype=torch.float64)
+    for k in range(table.shape[1]):
+        rows = torch.nonzero(table[:, k] >= 0)[:, 0]
+        if len(rows):
+            out[rows] += x[table[rows, k]] @ w[k]
+    return out + (bias.detach().cpu().double().view(1, -1) if bias is not None else 0)
+
+
 class OracleNet:
     """Forward pass of a canonicalvoting_b200.minkunet model on CPU through the functions above, reading the
     parameters from the model's state dict (BatchNorm in the model's train/eval mode)."""
@@ -89,14 +101,18 @@ class OracleNet:
     def __init__(self, model):
         self.m = model
 
+    def _p(self, t):
+        """A parameter of the model as the CPU tensor the restatement computes with."""
+        return t.detach().cpu()
+
     def _bn(self, mod, f):
         bn = mod.bn
-        return torch.nn.functional.batch_norm(f, bn.running_mean.cpu().clone(), bn.running_var.cpu().clone(), bn.weight.detach().cpu(),
-                                              bn.bias.detach().cpu(), bn.training, bn.momentum, bn.eps)
+        return torch.nn.functional.batch_norm(f, bn.running_mean.cpu().clone(), bn.running_var.cpu().clone(), self._p(bn.weight),
+                                              self._p(bn.bias), bn.training, bn.momentum, bn.eps)
 
     def _conv(self, mod, coords_by_ts, ts, f):
-        w = mod.kernel.detach().cpu()
-        b = mod.bias.detach().cpu() if mod.bias is not None else None
+        w = self._p(mod.kernel)
+        b = self._p(mod.bias) if mod.bias is not None else None
         if mod.kernel_size == 1:
             return ts, f @ w + (b if b is not None else 0)
         if mod.is_transpose:
@@ -202,8 +218,8 @@ class FastCpuNet(OracleNet):
     """OracleNet with vectorised maps (float32, torch CPU threads)."""
 
     def _conv(self, mod, maps, ts, f):
-        w = mod.kernel.detach().cpu()
-        b = mod.bias.detach().cpu() if mod.bias is not None else None
+        w = self._p(mod.kernel)
+        b = self._p(mod.bias) if mod.bias is not None else None
         cout = w.shape[-1]
         if mod.kernel_size == 1:
             return ts, f @ w + (b if b is not None else 0)
@@ -232,6 +248,31 @@ class FastCpuNet(OracleNet):
     def forward(self, coords, feats):
         self_maps = FastMaps(coords.cpu())
         return OracleNet.forward_with(self, self_maps, feats)
+
+
+class GradCpuNet(FastCpuNet):
+    """FastCpuNet whose parameters are float64 autograd leaves (copies of the model's): `forward` is then differentiable
+    by plain torch autograd, which gives reference parameter gradients for the training step (train_joint.py:284-286)
+    without any hand-written backward.  `grads()` maps the model's parameter names to the leaves' gradients."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.leaves = {}
+
+    def _p(self, t):
+        leaf = self.leaves.get(id(t))
+        if leaf is None:
+            leaf = t.detach().cpu().double().requires_grad_(True)
+            self.leaves[id(t)] = leaf
+        return leaf
+
+    def _bn(self, mod, f):
+        bn = mod.bn
+        return torch.nn.functional.batch_norm(f, bn.running_mean.cpu().double().clone(), bn.running_var.cpu().double().clone(),
+                                              self._p(bn.weight), self._p(bn.bias), bn.training, bn.momentum, bn.eps)
+
+    def grads(self):
+        return {name: self.leaves[id(p)].grad for name, p in self.m.named_parameters() if id(p) in self.leaves}
 
 
 def _forward_with(self, C, feats):

@@ -168,3 +168,37 @@ def test_fast_cpu_port_matches_dict_oracle():
     a = SO.OracleNet(model).forward(coords, feats)
     b = SO.FastCpuNet(model).forward(coords, feats)
     torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_grad_net_is_the_fast_net_with_autograd_leaves():
+    """GradCpuNet (the reference of the tf32 training-step test) = FastCpuNet in float64 with the parameters as autograd leaves:
+    same forward, and its gradients agree with central finite differences of the loss."""
+    from canonicalvoting_b200.minkunet import MinkUNet14A
+    torch.manual_seed(2)
+    g = torch.Generator().manual_seed(4)
+    lin = torch.randperm(48 ** 3, generator=g)[:1500]
+    coords = torch.stack([torch.zeros_like(lin), lin // (48 * 48), (lin // 48) % 48, lin % 48], 1).int()
+    feats = torch.randn(1500, 3, generator=g)
+    model = MinkUNet14A(3, 8).train()
+    net = SO.GradCpuNet(model)
+    out = net.forward(coords, feats.double())
+    with torch.no_grad():
+        f32 = SO.FastCpuNet(model).forward(coords, feats)
+    assert float((out.detach() - f32.double()).abs().max()) <= 1e-4 * float(f32.abs().max())
+    target = torch.randn(out.shape, generator=g).double()
+    loss = ((out - target) ** 2).mean()
+    loss.backward()
+    grads = net.grads()
+    assert set(grads) == {n for n, _ in model.named_parameters()} and all(v is not None for v in grads.values())
+    for name, idx in (("final.kernel", (3, 5)), ("block4.0.conv1.kernel", (13, 7, 9)), ("bn0.bn.weight", (4,))):
+        p = dict(model.named_parameters())[name]
+        eps, vals = 2e-4, []
+        for sgn in (1, -1):
+            with torch.no_grad():
+                p[idx] += sgn * eps
+            o = SO.GradCpuNet(model).forward(coords, feats.double())
+            vals.append(float(((o - target) ** 2).mean()))
+            with torch.no_grad():
+                p[idx] -= sgn * eps
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        assert abs(fd - float(grads[name][idx])) <= 2e-2 * max(abs(fd), 1e-3), (name, fd, float(grads[name][idx]))

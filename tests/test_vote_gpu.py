@@ -35,6 +35,8 @@ CASES = [
     ("ragged", dict(n=777, grid=20, num_rots=7, seed=2)),
     ("R120", dict(n=2000, grid=24, num_rots=120, seed=3)),                  # reference default R
     ("C2", dict(n=50000, grid=128, num_rots=12, seed=0)),                    # BASELINE configs[1] vote half
+    ("odd-grid", dict(n=6000, grid=37, num_rots=9, seed=5)),                 # grid edge not a multiple of the 8-voxel tile
+    ("C5", dict(n=200000, grid=256, num_rots=24, seed=0)),                   # BASELINE configs[4] vote half
 ]
 
 
@@ -154,8 +156,8 @@ def test_full_size_properties_C5():
         go3, gr3, gs3 = hv_cuda.forward(p, x, s, o, res_t, rots_t)
         assert_grid_close(go3.cpu().numpy(), go.cpu().numpy(), what="idempotence obj")
         assert_grid_close(gs3.cpu().numpy(), gs.cpu().numpy(), what="idempotence scale")
-    for w in H._work_cache.values():
-        assert not w.any(), "workspace not re-zeroed"
+    for w, _ in H._work_cache.values():
+        assert not w[:4 * 32 ** 3].any(), "tile counters not re-zeroed"
 
 
 def test_edge_cases():

@@ -50,10 +50,9 @@ cases_all = [("L1 3^3 96->96", cm.kernel_map(1, 3), cm.levels[1].n, 96, 96),
          ("L8 3^3 256->256", cm.kernel_map(8, 3), cm.levels[8].n, 256, 256),
          ("L16 3^3 256->256", cm.kernel_map(16, 3), cm.levels[16].n, 256, 256),
          ("L1 up 2^3 96->96", cm._down[1]["up_table"], cm.levels[2].n, 96, 96)]
-cases = cases_all[:1] + cases_all[2:3] + cases_all[4:5]
-modes = [(0, "normal"), (13, "barriers only"), (1, "no gather"), (4, "no MMA"), (8, "no weight TMA")]
+cases = cases_all if "all" in sys.argv else cases_all[:1] + cases_all[2:3] + cases_all[4:5]
+modes = [(0, "normal"), (13, "barriers only"), (1, "no gather"), (4, "no MMA"), (8, "no weight TMA"), (9, "MMA only"), (5, "weights only"), (12, "gather only"), (2, "no zero-fill copies")]
 for impl in (3,):
-    L.cvb200_sc_set_conv_impl(impl)
     for name, table, n_in, cin, cout in cases:
         pairs = int((table >= 0).sum())
         line = "impl %d %-18s rows %6d pairs %8d:" % (impl, name, table.shape[0], pairs)
@@ -65,7 +64,6 @@ for impl in (3,):
                 line += " (%.1f TF/s alg.)" % (2.0 * pairs * cin * cout / us / 1e6)
         L.cvb200_sc_set_conv_debug(0)
         print(line, flush=True)
-L.cvb200_sc_set_conv_impl(3)
 
 # pieces per split tile: planner's choice (0) vs forced
 for name, table, n_in, cin, cout in []:
