@@ -35,9 +35,10 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 NCLASSES = 9
-# DRAM bytes per call of the vote op from the ncu --set full capture of round 1 (scatter 21.03 MB read; write-out 67.13 MB read +
-# 15.25 MB written before the kernel ended), C2 scene only; None where no capture exists
-VOTE_DRAM_BYTES_NCU = {"C2": 21029376 + 8192 + 67128832 + 15247104}
+# DRAM bytes per call of the vote op (sum over its kernels) from this round's ncu --set full capture; None where no capture exists
+VOTE_DRAM_BYTES_NCU = {}
+# same for the convolution program (sum over its launches); filled in from this round's capture
+CONV_DRAM_BYTES_NCU = {}
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -226,20 +227,69 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def train_c3(args, dev, rank, world, local):
+    """BASELINE configs[2]/[3]: the training step (train_joint.py:244-288) on 8 synthetic 50k-voxel scenes per GPU -- MinkUNet34C
+    forward + joint loss + backward + Adam, convolutions / input gradients / weight gradients on tcgen05 (tf32 mode); under
+    torchrun DistributedDataParallel all-reduces the 37.9 M gradients (151 MB) over NCCL, overlapped with the backward pass.
+    Returns the extra object of the bench line (scenes/s over all ranks, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200 import synthetic, train
+    from canonicalvoting_b200.minkunet import MinkUNet34C
+    scenes_per_gpu, steps, warm = 8, args.train_steps, 2
+    ME.set_forward_mode("tf32")
+    try:
+        torch.manual_seed(0)
+        model = MinkUNet34C(3, 6 * NCLASSES + NCLASSES + 1).to(dev).train()
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        mine = train.shard_scenes(scenes_per_gpu * world, rank, world)
+        batch = train.collate([synthetic.make_scene(50000, 128, 12, seed=1000 + i) for i in mine])
+        for _ in range(warm):
+            loss = train.train_step(ddp, opt, batch, dev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = train.train_step(ddp, opt, batch, dev)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t) / steps
+        nparam = sum(p.numel() for p in model.parameters())
+        out = {"metric": "train_scenes_per_sec", "value": scenes_per_gpu * world / sec, "unit": "scenes/s", "ms_per_step": 1e3 * sec,
+               "steps": steps, "scenes_per_gpu": scenes_per_gpu, "rows_per_gpu": int(batch[0].shape[0]), "loss": float(loss),
+               "grad_allreduce_bytes": 4 * nparam if world > 1 else 0, "scaling": "weak",
+               "what": "config C3/C4: MinkUNet34C fwd + joint loss + bwd + Adam on 8 x 50k-voxel scenes per GPU, tf32 tcgen05 convolutions"
+                       + (", DDP/NCCL gradient all-reduce" if world > 1 else "")}
+        del ddp, opt, model, batch
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        ME.set_forward_mode("auto")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C5"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--streams", type=int, default=2, help="scenes in flight per GPU (one CUDA stream + host thread each)")
-    ap.add_argument("--e2e-streams", type=int, default=3, help="scenes in flight for the end-to-end measurement (more host syncs per scene)")
+    ap.add_argument("--streams", type=int, default=3, help="scenes in flight per GPU (one CUDA-graph lane + stream each)")
+    ap.add_argument("--train-steps", type=int, default=6, help="timed steps of the training workload (config C3/C4); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 1)
 
     if args.impl == "reference":
+        if args.steps > 30:
+            args.steps = 30          # the CPU arm is sized for a ~2 minute run; its per-step sample shrinks with the step count
         run_reference_arm(args)
         return
 
@@ -249,19 +299,24 @@ def main():
     import hv_cuda
     from canonicalvoting_b200 import hv_cuda as H
     from canonicalvoting_b200.engine import MinkUNetEngine
+    from canonicalvoting_b200.hough_voting import back_project
 
-    if os.environ.get("CVB200_CONV_OPTS"):      # A/B switch for measurements: "<allow_split>,<use_pdl>[,<impl>]"
+    if os.environ.get("CVB200_CONV_OPTS"):      # A/B switch for measurements: "<allow_split>,<use_pdl>"
         from canonicalvoting_b200 import _lib
         o = [int(x) for x in os.environ["CVB200_CONV_OPTS"].split(",")]
         _lib.load().cvb200_sc_set_conv_options(o[0], o[1])
-        if len(o) > 3:
-            _lib.load().cvb200_sc_set_conv_debug(o[3])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:       # one host thread per rank drives everything: keep the ranks of a node on separate cores
+        ncpu = os.cpu_count() or 1
+        per = max(1, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+        os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -271,7 +326,7 @@ def main():
     n, R, res = len(sc["points"]), sc["num_rots"], sc["res"]
     model_cpu = make_model()
     model = make_model().to(dev)
-    engine = MinkUNetEngine(model, NCLASSES, True, pipeline=True)
+    engine = MinkUNetEngine(model, NCLASSES, True)
     coords_h, feats_h = scene_tensors(sc)
     coords_h, feats_h = coords_h.pin_memory(), feats_h.pin_memory()
     coords_d, feats_d = coords_h.to(dev), feats_h.to(dev)
@@ -282,16 +337,15 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    thresh_high = 60.0 * R / 120           # eval_joint.py:18 assumes 120 rotations
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident step: U-Net program -> decode -> vote (grid geometry known on the host, no sync inside)
+    # ---- stage-by-stage step of ONE scene, L2 flushed: the roofline's kernel times (plain stream launches, no graph)
     def step_resident(marks=None):
-        """One scene, stage by stage (diagnostics for the roofline): the coordinate maps and the program are prepared first,
-        then L2 is flushed, then the convolution program, the decode and the vote op are timed with CUDA events."""
         cm = engine.build_maps(coords_d)
         arr, f, keep = engine.build(coords_d, feats_d, cm)
         flush.zero_()
@@ -308,8 +362,9 @@ def main():
             marks[3].record(stream)
         return out
 
-    # (1) throughput: K steps back to back over a rotation of resident scenes whose combined working set
-    #     (~200 MB each: activations, tables, vote workspace + grids) exceeds the 126 MB L2; CUDA events around the loop
+    # ---- (1) throughput: K scenes back to back over a rotation of resident scenes whose combined working set exceeds the 126 MB
+    #      L2.  One scene = ONE CUDA-graph launch (map builder + convolution program + decode + vote, SceneGraph) on one of
+    #      `--streams` lanes; a single host thread copies the scene into the lane's input buffers and replays.
     n_rot = 4
     scenes = [sc] + [scene_for(args.workload, seed=rank + world * (1 + j)) for j in range(n_rot - 1)]
     dev_scenes = []
@@ -318,64 +373,37 @@ def main():
         c_d, f_d = c_h.to(dev), f_h.to(dev)
         p_d = (c_d[:, 1:].float() * res).contiguous()
         cr, _, dm = H.grid_dims(p_d, res)
-        dev_scenes.append((c_d, f_d, cr, dm))
+        assert tuple(cr) == tuple(corner) and tuple(dm) == tuple(dims), "the synthetic scenes of a workload share the vote-grid geometry"
+        dev_scenes.append((c_d, f_d))
     torch.cuda.synchronize()
+    L = max(1, args.streams)
+    vote_cfg = dict(res=res, num_rots=R, corner=corner, dims=dims)
+    lanes = [engine.graph_lane(n, vote=vote_cfg) for _ in range(L)]
+    lanes_e2e = [engine.graph_lane(n) for _ in range(L)]                   # network + decode; the vote goes through hv_cuda.forward
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(L)]
+    host_s = [0.0, 0]
 
-    # `--streams` scenes are in flight per GPU: each stream has its own engine instance (activation arena, map side
-    # stream, prefetch worker) and is driven by its own host thread; the latency-bound small levels of one scene then
-    # overlap the other scene's work.  Stream 0 is the caller's stream.
-    n_streams = max(1, args.streams, args.e2e_streams)      # lanes that exist; run_lanes uses the first `active` of them
-    engines = [engine] + [MinkUNetEngine(model, NCLASSES, True, pipeline=True) for _ in range(n_streams - 1)]
-    lanes = [stream] + [torch.cuda.Stream(dev) for _ in range(n_streams - 1)]
-
-    def run_lanes(fn, k_total, n_streams=None):
-        """fn(lane, engine, first_scene, k) on `n_streams` lanes concurrently; returns seconds from the common start to the
-        last lane's end, measured with CUDA events on the lanes' streams."""
-        import threading as th
-        n_streams = max(1, n_streams if n_streams is not None else args.streams)
+    def run_value(k_total):
         start = ev()
         start.record(stream)
-        ends = [ev() for _ in range(n_streams)]
-        share = [k_total // n_streams + (1 if i < k_total % n_streams else 0) for i in range(n_streams)]
-        errs = []
-
-        def work(i):
-            try:
-                torch.cuda.set_device(local)
-                with torch.cuda.stream(lanes[i]):
-                    lanes[i].wait_event(start)
-                    fn(i, engines[i], sum(share[:i]), share[i])
-                    ends[i].record(lanes[i])
-            except BaseException as e:  # pragma: no cover
-                errs.append(e)
-        ts = [th.Thread(target=work, args=(i,)) for i in range(1, n_streams)]
-        for t_ in ts:
-            t_.start()
-        work(0)
-        for t_ in ts:
-            t_.join()
-        if errs:
-            raise errs[0]
+        for st in lane_streams:
+            st.wait_event(start)
+        t0 = time.perf_counter()
+        for j in range(k_total):
+            with torch.cuda.stream(lane_streams[j % L]):
+                lanes[j % L].run(*dev_scenes[j % n_rot])
+        host_s[0] += time.perf_counter() - t0
+        host_s[1] += k_total
+        ends = []
+        for st in lane_streams:
+            e_ = ev()
+            e_.record(st)
+            ends.append(e_)
         for e_ in ends:
             e_.synchronize()
         return max(start.elapsed_time(e_) for e_ in ends) / 1e3
 
-    def step_scene(eng, j, maps=None):
-        c_d, f_d, cr, dm = dev_scenes[j % n_rot]
-        xyz, scale, cls, prob, points = eng.predict(c_d, f_d, maps, res=res)   # points = coords * res (eval_joint.py:193), same kernel
-        return H.forward_host(points, xyz, scale, prob, res, R, cr, dm)
-
-    def run_steps(lane, eng, j0, k):
-        # the coordinate maps of scene j+1 are built by the engine's worker thread / side stream while scene j is launched
-        if k == 0:
-            return
-        fut = eng.prefetch(dev_scenes[j0 % n_rot][0])
-        for j in range(j0, j0 + k):
-            nxt = eng.prefetch(dev_scenes[(j + 1) % n_rot][0]) if j + 1 < j0 + k else None
-            step_scene(eng, j, fut)
-            fut = nxt
-
-    run_lanes(run_steps, args.warmup * max(1, args.streams) + n_rot)
+    run_value(args.warmup * L + n_rot)
     barrier()
     import gc
     gc.collect()
@@ -384,20 +412,22 @@ def main():
     with ClockSampler(local) as clk:
         t_attach = time.time()          # let nvidia-smi attach before the timed region -- with the GPU kept busy (an idle
         while time.time() - t_attach < 0.3:   # GPU drops its clocks and the first timed pass pays the ramp-up)
-            run_lanes(run_steps, 2 * max(1, args.streams))
+            run_value(4 * L)
         clk.mark()
+        host_s[0], host_s[1] = 0.0, 0
         for _ in range(3):              # K steps, three times back to back; every pass is reported, the median counts
-            passes.append(run_lanes(run_steps, args.steps))
+            passes.append(run_value(args.steps))
             barrier()
     gc.enable()
     t_resident = sorted(passes)[1]
+    host_us_per_scene = 1e6 * host_s[0] / max(host_s[1], 1)
 
-    # (2) diagnostics for the roofline: per-step CUDA events with an L2 flush (256 MiB write) between steps
+    # ---- (2) diagnostics for the roofline: per-step CUDA events with an L2 flush (256 MiB write) between steps
     for _ in range(3):
         step_resident()
     barrier()
     marks = []
-    for _ in range(min(args.steps, 10)):
+    for _ in range(10):
         m = [ev(), ev(), ev(), ev()]
         step_resident(m)
         marks.append(m)
@@ -406,32 +436,90 @@ def main():
     unet_ms = [m[0].elapsed_time(m[1]) for m in marks]
     vote_ms = [m[2].elapsed_time(m[3]) for m in marks]
 
-    # ---- end to end through the reference-facing API with HOST buffers
-    def step_e2e(eng, fut):
-        # fut: upload (pinned host -> device) + coordinate maps of THIS scene, started while the previous scene ran
-        c, f, _, _ = fut.result()
-        xyz, scale, cls, prob, points = eng.predict(None, None, fut, res=res)
-        go, gr, gs = hv_cuda.forward(points, xyz, scale, prob, res_t, rots_t)
-        peak = torch.stack([go.max(), go.argmax().float()])
-        return peak.cpu()          # D2H read of the step's result (peak value + voxel)
+    # ---- (3) end to end through the reference-facing API with HOST buffers, returning the product's result: H2D of the scene ->
+    #      network + decode (one graph launch) -> hv_cuda.forward (its grid-geometry sync included) -> candidate loop with the
+    #      LCC back-projection check (eval_joint.py:195-263) -> boxes / scores / classes copied to the host.  Single host thread,
+    #      software-pipelined over the lanes: the network of scene j + L - 1 is enqueued before scene j is finished.
+    d2h_bytes = [0, 0]
 
-    def run_e2e(lane, eng, j0, k):
-        if k == 0:
-            return
-        fut = eng.prefetch(coords_h, feats_h)
-        for j in range(k):
-            nxt = eng.prefetch(coords_h, feats_h) if j + 1 < k else None
-            step_e2e(eng, fut)
-            fut = nxt
+    def e2e_enqueue(j):
+        with torch.cuda.stream(lane_streams[j % L]):
+            return lanes_e2e[j % L].run(coords_h, feats_h)
 
-    run_lanes(run_e2e, args.warmup * max(1, args.e2e_streams), args.e2e_streams)
-    t_e2e = float("inf")
-    for _ in range(2):            # two passes of K steps, the steadier one counts (host jitter shows up here: 2 syncs per step)
+    def e2e_finish(j, o):
+        with torch.cuda.stream(lane_streams[j % L]):
+            go, gr, gs = hv_cuda.forward(o["points"], o["xyz"], o["scale"], o["prob"], res_t, rots_t)
+            boxes, scores, classes = back_project(go, gr, gs, o["points"], o["xyz"], o["prob"], o["class_pred"], res, corner=corner,
+                                                  thresh_high=thresh_high)
+            peak = torch.stack([go.max(), go.argmax().float()])
+            hb, hs, hc, hp = boxes.cpu(), scores.cpu(), classes.cpu(), peak.cpu()      # D2H of the step's result
+        d2h_bytes[0] += hb.numel() * 4 + hs.numel() * 4 + hc.numel() * 8 + 8 + 8 + 36    # + box count + peak + vote-grid geometry
+        d2h_bytes[1] += 1
+        return len(hb)
+
+    def run_e2e(k_total):
+        start = ev()
+        start.record(stream)
+        for st in lane_streams:
+            st.wait_event(start)
+        pend = {}
+        for j in range(min(L - 1, k_total)):
+            pend[j] = e2e_enqueue(j)
+        nb = 0
+        for j in range(k_total):
+            if j + L - 1 < k_total:
+                pend[j + L - 1] = e2e_enqueue(j + L - 1)
+            nb += e2e_finish(j, pend.pop(j))
+        ends = []
+        for st in lane_streams:
+            e_ = ev()
+            e_.record(st)
+            ends.append(e_)
+        for e_ in ends:
+            e_.synchronize()
+        return max(start.elapsed_time(e_) for e_ in ends) / 1e3, nb
+
+    run_e2e(args.warmup * L)
+    t_e2e, n_boxes = float("inf"), 0
+    for _ in range(2):            # two passes of K steps, the steadier one counts
         barrier()
-        t_e2e = min(t_e2e, run_lanes(run_e2e, args.steps, args.e2e_streams))
+        t_, n_boxes = run_e2e(args.steps)
+        t_e2e = min(t_e2e, t_)
         barrier()
     h2d = coords_h.numel() * 4 + feats_h.numel() * 4
-    d2h = 8 + 4 * 5 + 36                               # result + the level sizes of the map builder + the vote grid geometry (hv_cuda.forward)
+    d2h = d2h_bytes[0] / max(d2h_bytes[1], 1)
+
+    # ---- (3b) the UNCHANGED module call of eval_joint.py:169-171 -- model(ME.SparseTensor(feats, coords)).F -- timed the same way
+    #      (single scene at a time: that is how the script calls it), reported beside the engine
+    t_module = None
+    try:
+        from canonicalvoting_b200 import sparse as ME
+        with torch.no_grad():
+            for _ in range(3):
+                model(ME.SparseTensor(feats_d, coords_d, device=dev)).F
+            torch.cuda.synchronize()
+            m0, m1 = ev(), ev()
+            m0.record(stream)
+            for _ in range(10):
+                model(ME.SparseTensor(feats_d, coords_d, device=dev)).F
+            m1.record(stream)
+            torch.cuda.synchronize()
+            t_module = m0.elapsed_time(m1) / 10
+    except Exception as e:  # pragma: no cover
+        t_module = repr(e)
+
+    for ln in lanes + lanes_e2e:
+        del ln
+    lanes, lanes_e2e = [], []
+    torch.cuda.empty_cache()
+
+    # ---- (4) training workload (configs C3 / C4) on the same clock
+    train = None
+    if args.train_steps > 0:
+        try:
+            train = train_c3(args, dev, rank, world, local)
+        except Exception as e:  # pragma: no cover
+            train = {"error": repr(e)}
 
     # ---- max over ranks
     times = torch.tensor([t_resident, t_e2e], dtype=torch.float64, device=dev)
@@ -443,7 +531,7 @@ def main():
         hbm_gbs, bf16_tf, peak_src = load_peaks()
         # algorithmic FLOPs of the convolution program: 2 * pairs * cin * cout per op, pairs counted from the tables
         arr, _, keep = engine.build(coords_d, feats_d)
-        flops = program_flops(engine, keep[0], arr)
+        flops, executed = program_flops(engine, keep[0], arr)
         unet_med = float(np.median(unet_ms))
         vote_med = float(np.median(vote_ms))
         tflops = flops / (unet_med * 1e-3) / 1e12
@@ -469,28 +557,41 @@ def main():
                                                        "what": "unmodified hv_cuda.forward built for sm_100a (oracle/_ref)"}
         except Exception as e:  # pragma: no cover
             cpu["reference_vote_cuda_same_gpu"] = {"error": repr(e)}
+        launches_per_scene = len(arr) + 1 + 29 + 1 + 2      # convolutions, input pad, map builder, decode, vote (scatter, write-out)
+        ms_step = 1e3 * t_resident / args.steps
         line = {
             "metric": "scenes_per_sec", "value": world * args.steps / t_resident, "unit": "scenes/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "passes_ms_per_step": [1e3 * p_ / args.steps for p_ in passes],
             "step_ms_flushed": {"median": float(np.median(step_ms)), "min": float(np.min(step_ms)), "max": float(np.max(step_ms))},
+            "host_us_per_scene": host_us_per_scene,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (U-Net) / f32 (vote)",
-            "data": "synthetic", "config": dict(workload_config(args.workload, sc), scenes_in_flight_per_gpu=max(1, args.streams),
-                                              scenes_in_flight_per_gpu_e2e=max(1, args.e2e_streams)),
-            "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            # per step: the convolution program (63 persistent conv launches; + the 4-channel pad of the input), 29 kernels of the fused map builder
-            # (csrc/sparse_maps.cu), head decode, vote scatter + write-out  (ncu launch list: profiles/r1s_launches_bench_C2.csv)
-            "gpu_launches": (len(arr) + 1 + 29 + 3) * args.steps,
+            "data": "synthetic", "config": dict(workload_config(args.workload, sc), scenes_in_flight_per_gpu=L),
+            "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "result": "boxes [K,8,3] + scores + classes of the candidate loop (eval_joint.py:255-263) + vote-map peak; K = %.2f boxes per "
+                              "scene with these randomly initialised weights" % (n_boxes / max(args.steps, 1)),
+                    "module_api_ms_per_scene": t_module,
+                    "module_api_what": "the unchanged call of eval_joint.py:169-171, model(ME.SparseTensor(feats, coords)).F in eval mode under "
+                                       "no_grad (one scene at a time, device-resident inputs, network only); engine, same scope: "
+                                       "step_ms_flushed minus the vote"},
+            "gpu_launches": launches_per_scene * args.steps,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
-                         "traffic": None, "peak_source": peak_src + ": bf16 sustained / 2 (kind::tf32 runs at half the bf16 rate)",
-                         "kernel": "sc_conv_persist_kernel program of the U-Net (%d fused convolutions)" % len(arr),
-                         "algorithmic_flops": flops, "kernel_ms": unet_med,
+                         "traffic": CONV_DRAM_BYTES_NCU.get(args.workload),
+                         "traffic_source": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the convolution launches of one scene, "
+                                           "ncu capture of this round (profiles/)",
+                         "peak_source": peak_src + ": bf16 sustained / 2 (kind::tf32 runs at half the bf16 rate)",
+                         "kernel": "sc_conv_persist_kernel program of the U-Net (%d fused convolutions), one scene alone, L2 flushed" % len(arr),
+                         "algorithmic_flops": flops, "executed_flops": executed, "kernel_ms": unet_med,
+                         "in_flight": {"achieved": flops * world * args.steps / t_resident / 1e12 / world,
+                                       "what": "algorithmic FLOPs x scenes/s per GPU over the timed region (whole step incl. map builder, "
+                                               "decode and vote; %d scenes in flight): a lower bound of the program's throughput" % L},
                          "vote": {"bound": "hbm", "achieved": vote_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": vote_gbs / hbm_gbs,
                                   "kernel": "hv_scatter_kernel + hv_finalize_kernel", "algorithmic_bytes": vbytes,
                                   "kernel_ms": vote_med, "traffic": VOTE_DRAM_BYTES_NCU.get(args.workload),
-                                  "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two kernels, one ncu --set full "
-                                                    "capture (profiles/r1s_ncu_full_vote_raw.csv); outputs still in L2 at kernel end are not in it"}},
+                                  "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two kernels, ncu --set full capture of "
+                                                    "this round (profiles/)"}},
             "cpu_baseline": cpu,
+            "train_C3": train,
             "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)
@@ -499,9 +600,10 @@ def main():
 
 
 def program_flops(engine, cm, arr):
-    """2 * sum over ops of (existing (output, offset) pairs) * cin * cout."""
+    """(algorithmic, executed): 2 * sum over ops of (existing (output, offset) pairs) * cin * cout, and the FLOPs of the MMAs the
+    kernel actually issues -- every 128-row tile runs all K^3 offsets of all its rows (missing neighbours are zero rows)."""
     import torch
-    seen, total = {}, 0
+    seen, total, executed = {}, 0, 0
     tables = {t.data_ptr(): t for t in cm._nbr.values()}
     for d in cm._down.values():
         tables[d["children"].data_ptr()] = d["children"]
@@ -511,7 +613,9 @@ def program_flops(engine, cm, arr):
         if o.table not in seen:
             seen[o.table] = int((t >= 0).sum())
         total += 2 * seen[o.table] * (4 if o.kind == 3 else o.cin) * o.cout     # kind 3: 4-channel gather (cin field = padded K)
-    return total
+        rows = (o.n_out + 127) // 128 * 128
+        executed += 2 * rows * (o.cin if o.kind == 3 else o.k3 * o.cin) * o.cout       # kind 3: cin field = padded K = 32 * ceil(k3 / 8)
+    return total, executed
 
 
 if __name__ == "__main__":

@@ -21,8 +21,6 @@ SIGNATURES = {
     "cvb200_hv_grid_dims": (ctypes.c_int, [_f, _i64, ctypes.c_float, _vp, ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i32), _vp]),
     "cvb200_hv_forward_work_bytes": (ctypes.c_size_t, [ctypes.POINTER(_i32)]),
-    "cvb200_hv_forward_work_bytes_n": (ctypes.c_size_t, [ctypes.POINTER(_i32), _i64, _i32]),
-    "cvb200_hv_set_impl": (ctypes.c_int, [_i32]),
     "cvb200_hv_forward": (ctypes.c_int, [_f, _f, _f, _f, _i64, ctypes.c_float, _i32, ctypes.POINTER(ctypes.c_float),
                                           ctypes.POINTER(_i32), _f, _f, _f, _vp, ctypes.c_size_t, _vp]),
     "cvb200_hv_backward": (ctypes.c_int, [_f, _f, _f, _f, _f, _i64, ctypes.c_float, _i32,

@@ -377,9 +377,11 @@ extern "C" int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, c
     int *ndirty = dirty + nb;
     CVB_CUDA(cudaMemsetAsync(ndirty, 0, 2 * sizeof(int), stream));
     // 16 CTAs per cluster (non-portable size, one GPC) when the device schedules it and the scene is large; 8 otherwise
-    static int max16 = -1;
-    if (max16 < 0) {
-        max16 = 0;
+    static DeviceOnce probed;                    // per device: the attribute and the occupancy answer belong to its context
+    static std::atomic<int> can16[256];
+    const int dev_id = DeviceOnce::device();
+    if (!probed.done()) {
+        int max16 = 0;
         if (cudaFuncSetAttribute(bp_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
             cudaLaunchConfig_t q = {};
             q.gridDim = dim3(16);
@@ -392,8 +394,10 @@ extern "C" int cvb200_back_project(float *d_grid_obj, const float *d_grid_rot, c
             if (cudaOccupancyMaxActiveClusters(&nclusters, bp_loop_kernel, &q) == cudaSuccess && nclusters >= 1) max16 = 1;
         }
         (void)cudaGetLastError();
+        can16[dev_id].store(max16);
+        probed.mark();
     }
-    const int csize = (max16 == 1 && n >= 30000) ? 16 : kBpCluster;
+    const int csize = (can16[dev_id].load() == 1 && n >= 30000) ? 16 : kBpCluster;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(csize);
     cfg.blockDim = dim3(kBpThreads);

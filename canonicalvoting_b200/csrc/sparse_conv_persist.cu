@@ -631,10 +631,10 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     alignas(64) CUtensorMap map_b;
     if (int rc = make_map_2d(&map_b, d_wt, (uint64_t)cin, (uint64_t)k3 * cout, (uint64_t)cin * 4, kPsKB, (uint32_t)P.nc)) return rc;
     const size_t smem = 1024 + 16384 + (size_t)P.stages * (kPsM * 128 + P.nc * 128);
-    static bool set = false;
-    if (!set) {
+    static DeviceOnce once;
+    if (!once.done()) {
         CVB_CUDA(cudaFuncSetAttribute(sc_conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemBytes));
-        set = true;
+        once.mark();
     }
     cudaLaunchConfig_t cfg = {};
     const int slots = kNumSMs * ctas_per_sm;

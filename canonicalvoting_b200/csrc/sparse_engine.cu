@@ -128,10 +128,10 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
                         "sc_run_program: op %d: small-cin convolution needs cin <= 8, cout in {32,64,96,128}, no residual", i);
             const size_t smem = sizeof(float) * (size_t)o.k3 * o.cin * o.cout;
             CVB_REQUIRE(smem <= 160 * 1024, CVB200_EINVAL, "sc_run_program: op %d: kernel does not fit shared memory", i);
-            static bool set = false;
-            if (!set) {
+            static DeviceOnce once;
+            if (!once.done()) {
                 CVB_CUDA(cudaFuncSetAttribute(sc_conv_smallcin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                set = true;
+                once.mark();
             }
             if (o.n_out > 0) {
                 const int blocks = (int)std::min<int64_t>(2 * kNumSMs, ceil_div(o.n_out, kStemThreads / 32));

@@ -249,10 +249,10 @@ int launch_wgrad_tc(const float *d_x, int cin, const float *d_dout, int cout, co
     P.stages = (223 * 1024) / stage_bytes;
     if (P.stages > kWtStages) P.stages = kWtStages;
     const size_t smem = 1024 + (size_t)P.stages * stage_bytes;
-    static bool set = false;
-    if (!set) {
+    static DeviceOnce once;
+    if (!once.done()) {
         CVB_CUDA(cudaFuncSetAttribute(sc_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        set = true;
+        once.mark();
     }
     const int grid = P.n_units < kNumSMs ? P.n_units : kNumSMs;
     sc_wgrad_tc_kernel<<<grid, kWtThreads, smem, stream>>>(map_b, d_x, cin, cin, cout, (const int *)d_table, (int)n_rows, k3, d_dw, P);

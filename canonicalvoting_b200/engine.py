@@ -109,6 +109,7 @@ class MinkUNetEngine:
         self._ring = collections.deque()      # (tensors used by launches in flight, completion event)
         self._pool = None                     # one worker thread for prefetch()
         self._pinned = None                   # count read-back buffer of the fused map builder (one build at a time)
+        self._cm_building = None
         self.fused_maps = True                # cvb200_sc_build_maps (one sync per scene); False: step-by-step coordinate manager
         self.stem_gather4 = os.environ.get("CVB200_STEM_IM2COL", "0") != "1"   # False: stem as im2col + product (refresh() after changing)
         self.refresh()
@@ -190,9 +191,10 @@ class MinkUNetEngine:
         self.out_channels = m.final.out_channels
 
     # ------------------------------------------------------------------ program construction
-    def _op(self, ops, name, src, dst, table, relu, residual=None):
+    def _op(self, ops, name, src, dst, table, relu, residual=None, out_ts=1):
         """Append one fused convolution; slice base addresses are arena offsets until the arena is committed, so the
-        pointer fields are filled in by build() afterwards (ops keep references to their slices)."""
+        pointer fields are filled in by build() afterwards (ops keep references to their slices).  `out_ts` = tensor stride of
+        the OUTPUT rows: with a size-agnostic coordinate manager the op reads that level's row count from device memory."""
         w, b, kind = self.w[name]
         k3 = w.shape[0]
         cin, cout = (w.shape[2], w.shape[1]) if kind == 0 else (w.shape[1], w.shape[2])
@@ -203,7 +205,12 @@ class MinkUNetEngine:
         o.n_out = table.shape[0]
         o.n_in = src.rows
         o.w, o.bias, o.table = w.data_ptr(), b.data_ptr() if b is not None else None, table.data_ptr()
+        o.n_out_dev = self._count_ptr(out_ts)
         ops.append((o, src, dst, residual))
+
+    def _count_ptr(self, ts):
+        cm = self._cm_building
+        return cm.count_ptr(ts.bit_length() - 1) if getattr(cm, "static", False) else None
 
     def _blocks(self, ops, arena, block, cm, ts, x, out_slice=None):
         """BasicBlocks of one stage; the last block writes into `out_slice` (a skip slot) when given."""
@@ -213,13 +220,13 @@ class MinkUNetEngine:
         ident = self._identity(cm, ts)
         for i in range(nblk):
             t1 = arena.matrix(n, planes)
-            self._op(ops, "%s.%d.conv1" % (block, i), x, t1, nbr, relu=True)
+            self._op(ops, "%s.%d.conv1" % (block, i), x, t1, nbr, relu=True, out_ts=ts)
             res = x
             if ("%s.%d.down" % (block, i)) in self.w:
                 res = arena.matrix(n, planes)
-                self._op(ops, "%s.%d.down" % (block, i), x, res, ident, relu=False)
+                self._op(ops, "%s.%d.down" % (block, i), x, res, ident, relu=False, out_ts=ts)
             dst = out_slice if (i == nblk - 1 and out_slice is not None) else arena.matrix(n, planes)
-            self._op(ops, "%s.%d.conv2" % (block, i), t1, dst, nbr, relu=True, residual=res)
+            self._op(ops, "%s.%d.conv2" % (block, i), t1, dst, nbr, relu=True, residual=res, out_ts=ts)
             x = dst
         return x
 
@@ -250,6 +257,7 @@ class MinkUNetEngine:
         """Buffers + program for one batch of scenes. Returns (ops array, output tensor [N, Cout], keep-alive list)."""
         if cm is None:
             cm = self.build_maps(coords)
+        self._cm_building = cm
         ts_list = [1, 2, 4, 8, 16]
         n = {ts: cm.levels[ts].n for ts in ts_list}
         P = self.planes
@@ -267,12 +275,14 @@ class MinkUNetEngine:
         stem_table = cm.kernel_map(1, self.model.conv0p1s1.kernel_size)
         if "conv0p1s1" in self.gather4:
             k3, cin, kp = self.gather4["conv0p1s1"]
-            feats4 = torch.nn.functional.pad(feats, (0, 4 - cin)).contiguous()        # [N, 4]: one 16-byte vector per voxel
+            # [N, 4]: one 16-byte vector per voxel (a caller that already holds the padded matrix passes it as is)
+            feats4 = feats if feats.shape[1] == 4 and cin < 4 else torch.nn.functional.pad(feats, (0, 4 - cin)).contiguous()
             w, b, _ = self.w["conv0p1s1"]
             o = _lib.ScOp()
             o.kind, o.cin, o.cout, o.k3, o.ldi, o.ldo, o.ldr, o.relu = 3, kp, w.shape[1], k3, 4, skip[1].ld, 0, 1
             o.n_out, o.n_in = n[1], feats4.shape[0]
             o.w, o.bias, o.table = w.data_ptr(), b.data_ptr() if b is not None else None, stem_table.data_ptr()
+            o.n_out_dev = self._count_ptr(1)
             src4 = _Slice(feats4.data_ptr(), feats4.shape[0], 4, 0, 4)
             ops.append((o, src4, skip[1], None))
             feats = feats4                     # kept alive with the program
@@ -290,18 +300,19 @@ class MinkUNetEngine:
         for (conv, bn, block), skip_ts in zip(_ENCODER, (2, 4, 8, None)):
             d = cm.down(ts)
             y = arena.matrix(n[2 * ts], self.w[conv][0].shape[1])
-            self._op(ops, conv, x, y, d["children"], relu=True)
+            self._op(ops, conv, x, y, d["children"], relu=True, out_ts=2 * ts)
             ts *= 2
             x = self._blocks(ops, arena, block, cm, ts, y, skip[skip_ts] if skip_ts is not None else None)
         for (conv, bn, block), fine in zip(_DECODER, (8, 4, 2, 1)):
             d = cm._down[fine]
             up = cat[fine].cols(0, tr_out[fine])
             arena.items.append(up)
-            self._op(ops, conv, x, up, d["up_table"], relu=True)
+            self._op(ops, conv, x, up, d["up_table"], relu=True, out_ts=fine)
             ts = fine
             x = self._blocks(ops, arena, block, cm, ts, cat[fine])
         out = arena.matrix(n[1], self.w["final"][0].shape[1])          # padded to a multiple of 16 channels
-        self._op(ops, "final", x, out, self._identity(cm, 1), relu=False)
+        self._op(ops, "final", x, out, self._identity(cm, 1), relu=False, out_ts=1)
+        self._cm_building = None
         buf = arena.commit()
         arr = (_lib.ScOp * len(ops))()
         for i, (o, src_, dst_, res_) in enumerate(ops):
@@ -384,6 +395,12 @@ class MinkUNetEngine:
         prob = torch.softmax(feats[:, 6:8], dim=-1)[:, 1].contiguous()
         return xyz, scale.contiguous(), prob
 
+    def graph_lane(self, n_voxels, vote=None):
+        """A `SceneGraph` for scenes of exactly `n_voxels` voxels: persistent input / table / activation / output buffers and ONE
+        captured CUDA graph holding the coordinate-map builder, the whole convolution program, the head decode (+ scan_points)
+        and -- with `vote=dict(res=, num_rots=, corner=, dims=)` -- the vote op.  See SceneGraph."""
+        return SceneGraph(self, int(n_voxels), vote)
+
     def predict(self, coords, feats, maps=None, res=None):
         """Network + head decode.  With `res` the tuple has a fifth element: scan_points = coords[:, 1:] * res."""
         if res is None:
@@ -391,3 +408,100 @@ class MinkUNetEngine:
         if maps is not None:
             coords = maps.result()[0]
         return self.decode(self(coords, feats, maps), coords, res)
+
+
+class SceneGraph:
+    """One scene = one CUDA-graph launch, no host synchronisation, no per-scene host work beyond two input copies.
+
+    The reference's per-scene host loop (eval_joint.py:160-193: build the sparse tensor, ~2000 MinkowskiEngine launches, ten
+    torch ops of decode glue) became, in round 1, ~100 launches + one count read-back issued by two Python threads per scene
+    -- still ~1.8 ms of host time per 1.5 ms of GPU time, which is what limited 8 ranks on one 32-core host.  Here nothing
+    the host enqueues depends on the scene: tables and activations are sized for the upper bound (a coarse level never has
+    more voxels than the input), the real level sizes stay in device memory where the map builder writes them and every
+    convolution reads its own row count and plans its tiles itself (cvb200_sc_op.n_out_dev).  So the whole sequence is
+    captured once per voxel count and replayed.
+
+        lane = engine.graph_lane(50000, vote=dict(res=0.03, num_rots=12, corner=(0, 0, 0), dims=(128, 128, 128)))
+        out = lane.run(coords, feats)          # host (pinned) or device tensors; asynchronous on the current stream
+        out["xyz"], out["scale"], out["class_pred"], out["prob"], out["points"], out["grids"], out["feats"]
+
+    The returned tensors are the lane's persistent buffers: they are overwritten by the lane's next run (stream-ordered), so
+    use one lane per scene in flight.  Memory is what the upper bounds cost: ~2 GB per lane at 50 000 voxels."""
+
+    def __init__(self, engine, n, vote=None):
+        from . import hv_cuda as H
+        self.engine, self.n, self.vote = engine, n, vote
+        dev = engine.device
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            self.coords = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+            self.feats_in = torch.zeros((n, engine.model.conv0p1s1.in_channels), dtype=torch.float32, device=dev)
+            pad4 = "conv0p1s1" in engine.gather4
+            self.feats4 = torch.zeros((n, 4), dtype=torch.float32, device=dev) if pad4 else self.feats_in
+            self.cm = CoordinateManager.static_unet(self.coords, int(engine.model.conv0p1s1.kernel_size), 4)
+            arr, out, keep = engine.build(self.coords, self.feats4, self.cm)
+            self.arr, self.out_full, self.keep = arr, out, keep
+            f32 = dict(dtype=torch.float32, device=dev)
+            self.xyz, self.scale = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
+            self.cls, self.prob = torch.empty((n,), dtype=torch.int64, device=dev), torch.empty((n,), **f32)
+            self.points = torch.empty((n, 3), **f32)
+            self.res = float(vote["res"]) if vote else 0.03
+            self.grids = None
+            if vote:
+                X, Y, Z = (int(d) for d in vote["dims"])
+                self.grids = (torch.empty((X, Y, Z), **f32), torch.empty((X, Y, Z, 2), **f32), torch.empty((X, Y, Z, 3), **f32))
+            self.stream = torch.cuda.Stream(dev)
+
+            def body():
+                if pad4:
+                    self.feats4[:, :self.feats_in.shape[1]].copy_(self.feats_in)
+                self.cm.enqueue()
+                _lib.check(L.cvb200_sc_run_program(arr, len(arr), _stream()), "cvb200_sc_run_program")
+                rc = L.cvb200_head_decode_points(_ptr(out), out.stride(0), n, engine.nclasses, 1 if engine.log_scale else 0, _ptr(self.xyz),
+                                                 _ptr(self.scale), _ptr(self.cls), _ptr(self.prob), _ptr(self.coords),
+                                                 ctypes.c_float(self.res), _ptr(self.points), _stream())
+                _lib.check(rc, "cvb200_head_decode_points")
+                if vote:
+                    work = H._workspace(L, vote["dims"], dev)
+                    rc = L.cvb200_hv_forward(_ptr(self.points), _ptr(self.xyz), _ptr(self.scale), _ptr(self.prob), n, self.res,
+                                             int(vote["num_rots"]), _lib.f3(vote["corner"]), _lib.i3(vote["dims"]), _ptr(self.grids[0]),
+                                             _ptr(self.grids[1]), _ptr(self.grids[2]), _ptr(work), work.numel(), _stream())
+                    _lib.check(rc, "cvb200_hv_forward")
+
+            # warm-up on the capture stream (per-stream scratch allocations, function attributes), then capture
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                body()
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            self.pdl = True
+            try:
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    body()
+            except Exception:
+                # a driver that cannot capture programmatic dependent launches: capture plain stream-ordered launches instead
+                torch.cuda.synchronize()
+                self.pdl = False
+                L.cvb200_sc_set_conv_options(1, 0)
+                try:
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph, stream=self.stream):
+                        body()
+                finally:
+                    L.cvb200_sc_set_conv_options(1, 1)
+        self.launches = len(arr) + 29 + 1 + (1 if pad4 else 0) + (2 if vote else 0)
+
+    def run(self, coords, feats):
+        """Copy one scene's inputs (int32 [n,4] coordinates, float32 [n,C] features; pinned host or device tensors) into the
+        lane's buffers and replay the graph on the current stream.  Returns the lane's output tensors (see class docstring)."""
+        if coords.shape[0] != self.n:
+            raise RuntimeError("SceneGraph built for %d voxels, got %d" % (self.n, coords.shape[0]))
+        self.coords.copy_(coords, non_blocking=True)
+        self.feats_in.copy_(feats, non_blocking=True)
+        self.graph.replay()
+        return {"feats": self.out_full, "xyz": self.xyz, "scale": self.scale, "class_pred": self.cls, "prob": self.prob,
+                "points": self.points, "grids": self.grids}
+
+    def level_counts(self):
+        """Voxels per level of the lane's last scene (synchronises; diagnostics / tests)."""
+        return [int(v) for v in self.cm.counts.cpu().tolist()]

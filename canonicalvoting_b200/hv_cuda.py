@@ -78,33 +78,16 @@ def grid_dims(points, res):
     return tuple(corner), tuple(maxpt), tuple(dims)
 
 
-def _workspace(L, dims, n, num_rots, device):
-    """Zero-filled ONCE per (device, stream); cvb200_hv_forward leaves the words it needs zero again (include/cvb200.h
-    contract), so the workspace is reused call after call.  The layout of its header depends on the number of tiles:
-    when the grid size changes the old header is wiped first."""
-    need = max(L.cvb200_hv_forward_work_bytes_n(_lib.i3(dims), int(n), int(num_rots)),
-               L.cvb200_hv_forward_work_bytes(_lib.i3(dims)) if _legacy_impl else 0)
-    header = L.cvb200_hv_forward_work_bytes_n(_lib.i3(dims), 0, 1)
+def _workspace(L, dims, device):
+    """Zero-filled ONCE per (device, stream); cvb200_hv_forward leaves it all-zero again
+    (include/cvb200.h contract), so a larger workspace is reused for smaller grids."""
+    need = L.cvb200_hv_forward_work_bytes(_lib.i3(dims))
     key = (device.index, torch._C._cuda_getCurrentRawStream(device.index))
-    ent = _work_cache.get(key)
-    if ent is None or ent[0].numel() < need:
-        ent = [torch.zeros(need, dtype=torch.uint8, device=device), header]
-        _work_cache[key] = ent
-    elif ent[1] != header:
-        ent[0][:max(ent[1], header)].zero_()
-        ent[1] = header
-    return ent[0]
-
-
-_legacy_impl = False
-
-
-def set_impl(sorted_tiles=True):
-    """Measurement aid: False selects the round-1 forward (vector reductions + write-out pass)."""
-    global _legacy_impl
-    _legacy_impl = not sorted_tiles
-    _work_cache.clear()
-    _lib.load().cvb200_hv_set_impl(1 if sorted_tiles else 0)
+    w = _work_cache.get(key)
+    if w is None or w.numel() < need:
+        w = torch.zeros(need, dtype=torch.uint8, device=device)
+        _work_cache[key] = w
+    return w
 
 
 def forward_host(points, xyz, scale, obj, res, num_rots, corner, dims):
@@ -115,7 +98,7 @@ def forward_host(points, xyz, scale, obj, res, num_rots, corner, dims):
     grid_obj = torch.empty((X, Y, Z), **opts)
     grid_rot = torch.empty((X, Y, Z, 2), **opts)
     grid_scale = torch.empty((X, Y, Z, 3), **opts)
-    work = _workspace(L, dims, points.shape[0], num_rots, points.device)
+    work = _workspace(L, dims, points.device)
     rc = L.cvb200_hv_forward(_ptr(points), _ptr(xyz), _ptr(scale), _ptr(obj), points.shape[0], float(res),
                              int(num_rots), _lib.f3(corner), _lib.i3(dims), _ptr(grid_obj), _ptr(grid_rot),
                              _ptr(grid_scale), _ptr(work), work.numel(), _stream_ptr())

@@ -58,6 +58,10 @@ class CoordinateManager:
         self.levels = {1: Level(coords.contiguous(), 1)}
         self._nbr = {}      # (tensor_stride, ksize) -> [n, ksize^3] int32
         self._down = {}     # fine tensor_stride -> dict(children, up_table, parent, koff)
+        # Inference (autograd off): the first map a layer asks for triggers ONE fused build of everything a U-Net needs (four
+        # stride-2 levels, their 3^3 maps, children / parent tables) with one host synchronisation, instead of a read-back per
+        # level; whatever a network asks beyond that is still built step by step on the same hash tables.
+        self._lazy_unet = not torch.is_grad_enabled()
 
     # ------------------------------------------------------------------ everything a U-Net needs, one enqueue + one sync
     @classmethod
@@ -67,6 +71,12 @@ class CoordinateManager:
         current stream and ONE synchronisation of it -- instead of a host read-back per level.  The result behaves like a
         manager on which kernel_map() / down() were already called (same tables, same numbering)."""
         cm = cls(coords)
+        cm._lazy_unet = False
+        cm._fill_unet(stem_ksize, n_down, pinned_counts)
+        return cm
+
+    def _fill_unet(self, stem_ksize, n_down=4, pinned_counts=None):
+        cm = self
         L = _lib.load()
         n = cm.levels[1].n
         lay = _lib.MapsLayout()
@@ -108,10 +118,70 @@ class CoordinateManager:
         for l in range(n_down):
             cm._down[1 << l] = dict(children=view(lay.children[l], counts[l + 1], 8), up_table=view(lay.up_table[l], counts[l], 8),
                                     parent=view(lay.parent[l], counts[l], 0), koff=view(lay.koff[l], counts[l], 0))
+
+    def _maybe_fill_unet(self, tensor_stride, ksize):
+        if self._lazy_unet:
+            self._lazy_unet = False
+            if self.levels[1].n >= 64 and not self._nbr and not self._down:
+                stem = ksize if (tensor_stride == 1 and ksize % 2 == 1 and 3 < ksize <= 7) else 0
+                self._fill_unet(stem, 4)
+
+    @classmethod
+    def static_unet(cls, coords, stem_ksize, n_down=4):
+        """Size-agnostic variant of build_unet for CUDA-graph capture: every level and table is a view of `n` rows (the upper
+        bound: a coarse level never has more voxels than the input), the real sizes stay in the device array `counts` that the
+        kernels read (cvb200_sc_op.n_out_dev) -- no host synchronisation, nothing depends on a size the host would have to
+        know.  `coords` is the caller's persistent int32 [n,4] input buffer; `enqueue()` (re)builds everything for its current
+        contents on the current stream.  `count_ptr(level)` is the device address of level 2^level's row count."""
+        cm = cls(coords)
+        L = _lib.load()
+        n = cm.levels[1].n
+        lay = _lib.MapsLayout()
+        _lib.check(L.cvb200_sc_maps_layout(n, stem_ksize, n_down, ctypes.byref(lay)), "cvb200_sc_maps_layout")
+        dev = cm.device
+        with torch.cuda.device(dev):
+            ws = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
+        pinned = torch.empty(8, dtype=torch.int32).pin_memory()
+
+        def view(off, rows, cols, dtype=torch.int32):
+            nbytes = rows * max(cols, 1) * (8 if dtype == torch.int64 else 4)
+            t = ws[off:off + nbytes].view(dtype)
+            return t.view(rows, cols) if cols else t
+
+        cm._ws, cm._pinned_counts, cm.static = ws, pinned, True
+        arange = view(lay.arange, n, 1)
+        for l in range(n_down + 1):
+            ts = 1 << l
+            if l:
+                lv = Level.__new__(Level)
+                lv.coords, lv.n, lv.tensor_stride = view(lay.coords[l], n, 4), n, ts
+                cm.levels[ts] = lv
+            lv = cm.levels[ts]
+            lv.capacity = int(lay.capacity)
+            lv.keys = view(lay.keys[l], lv.capacity, 0, torch.int64)
+            lv.vals = view(lay.vals[l], lv.capacity, 0)
+            lv.table_built = True
+            cm._nbr[(ts, 3)] = view(lay.nbr3[l], n, 27)
+            cm._nbr[("ident", ts)] = arange
+        if stem_ksize:
+            cm._nbr[(1, stem_ksize)] = view(lay.stem_table, n, stem_ksize ** 3)
+        for l in range(n_down):
+            cm._down[1 << l] = dict(children=view(lay.children[l], n, 8), up_table=view(lay.up_table[l], n, 8),
+                                    parent=view(lay.parent[l], n, 0), koff=view(lay.koff[l], n, 0))
+        counts_base = ws.data_ptr() + lay.counts
+        cm.count_ptr = lambda level: counts_base + 4 * level
+        cm.counts = view(lay.counts, n_down + 1, 0)
+
+        def enqueue():
+            rc = L.cvb200_sc_build_maps(_ptr(cm.levels[1].coords), n, stem_ksize, n_down, _ptr(ws), ctypes.byref(lay),
+                                        ctypes.c_void_p(pinned.data_ptr()), _stream())
+            _lib.check(rc, "cvb200_sc_build_maps")
+        cm.enqueue = enqueue
         return cm
 
     # ------------------------------------------------------------------ stride-1 kernel maps
     def kernel_map(self, tensor_stride, ksize):
+        self._maybe_fill_unet(tensor_stride, ksize)
         key = (tensor_stride, ksize)
         nbr = self._nbr.get(key)
         if nbr is None:
@@ -129,6 +199,7 @@ class CoordinateManager:
     # ------------------------------------------------------------------ stride-2 down / up maps
     def down(self, tensor_stride):
         """Maps between the level `tensor_stride` (fine) and 2*tensor_stride (coarse); creates the coarse level."""
+        self._maybe_fill_unet(tensor_stride, 0)
         d = self._down.get(tensor_stride)
         if d is None:
             L = _lib.load()

@@ -19,17 +19,18 @@ import torch
 from .. import _lib
 from .coords import _ptr, _stream
 
-# "fp32": CUDA-core implicit GEMM, exact fp32 accumulation (parity mode, always used for gradients)
+# "fp32": CUDA-core implicit GEMM, exact fp32 accumulation (parity mode)
 # "tf32": tcgen05 tensor-core implicit GEMM (kind::tf32, fp32 accumulate in TMEM) for forward, input and weight gradient
-_FORWARD_MODE = "fp32"
+# "auto" (default): tf32 where autograd is off -- the unchanged inference call of the reference scripts, `with torch.no_grad():
+#         model(ME.SparseTensor(...))` (eval_joint.py:160-171), lands on the tensor cores -- and fp32 where a graph is recorded
+#         (training keeps exact fp32 gradients unless the caller asks for tf32, as tools/bench_train.py and bench.py do)
+_FORWARD_MODE = "auto"
 
 
 def set_forward_mode(mode):
     global _FORWARD_MODE
-    if mode not in ("fp32", "tf32"):
-        raise ValueError("mode must be 'fp32' or 'tf32'")
-    if mode == "tf32" and not hasattr(_lib.load(), "cvb200_sc_conv_forward_tc"):
-        raise RuntimeError("libcvb200.so was built without the tensor-core convolution")
+    if mode not in ("fp32", "tf32", "auto"):
+        raise ValueError("mode must be 'fp32', 'tf32' or 'auto'")
     _FORWARD_MODE = mode
 
 
@@ -37,23 +38,67 @@ def get_forward_mode():
     return _FORWARD_MODE
 
 
-def conv_table_forward(x, w, table, bias=None, mode=None):
-    """x [n_in,cin] f32, w [K3,cin,cout] f32, table [n_out,K3] i32 -> [n_out,cout] f32."""
+def resolve_mode(mode=None):
+    """The arithmetic a convolution issued NOW uses: an explicit `mode`, else the global setting, 'auto' decided by autograd."""
+    mode = mode or _FORWARD_MODE
+    if mode == "auto":
+        return "fp32" if torch.is_grad_enabled() else "tf32"
+    return mode
+
+
+def _tc_ok(cin, cout, k3):
+    return cin % 32 == 0 and cout % 16 == 0 and 16 <= cout <= 512 and k3 <= 32
+
+
+def packed_weight(w):
+    """[K3, cin, cout] -> [K3, cout, cin] contiguous, the K-major B operand of the tensor-core kernel.  The copy is remembered on
+    the tensor object together with its version counter: an inference loop packs every kernel once, a training loop once per
+    optimizer step (the in-place parameter update bumps the version) instead of once per call."""
+    tag = getattr(w, "_cvb200_packed", None)
+    if tag is not None and tag[0] == w._version and tag[1].device == w.device:
+        return tag[1]
+    wt = w.detach().transpose(1, 2).contiguous()
+    try:
+        w._cvb200_packed = (w._version, wt)
+    except Exception:
+        pass
+    return wt
+
+
+def mirrored_table(table):
+    """A stride-1 kernel map with the offset axis reversed: the transposed map of a centred odd kernel (offset k <-> K^3-1-k),
+    which lets the input gradient use the weights as they are.  Remembered on the table object (one copy per scene and map)."""
+    m = getattr(table, "_cvb200_mirror", None)
+    if m is None:
+        m = table.flip(1).contiguous()
+        try:
+            table._cvb200_mirror = m
+        except Exception:
+            pass
+    return m
+
+
+def conv_table_forward(x, w, table, bias=None, mode=None, wt=None):
+    """x [n_in,cin] f32, w [K3,cin,cout] f32, table [n_out,K3] i32 -> [n_out,cout] f32.  `wt` (tf32 mode): the weight already as
+    [K3, cout, cin] (then `w` may be None)."""
     L = _lib.load()
     n_out, k3 = table.shape
-    cin, cout = w.shape[1], w.shape[2]
-    assert x.is_cuda and x.dtype == torch.float32 and x.shape[1] == cin and w.shape[0] == k3
-    x, w = x.contiguous(), w.contiguous()
+    cin, cout = (wt.shape[2], wt.shape[1]) if wt is not None else (w.shape[1], w.shape[2])
+    assert x.is_cuda and x.dtype == torch.float32 and x.shape[1] == cin and (wt if wt is not None else w).shape[0] == k3
+    x = x.contiguous()
     out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     b = bias.contiguous().view(-1) if bias is not None else None
-    mode = mode or _FORWARD_MODE
+    mode = resolve_mode(mode)
     with torch.cuda.device(x.device):
-        if mode == "tf32" and cin % 32 == 0 and cout % 16 == 0 and 16 <= cout <= 256 and k3 <= 32:
-            wt = w.transpose(1, 2).contiguous()     # [k3, cout, cin]: K-major B operand
+        if mode == "tf32" and _tc_ok(cin, cout, k3):
+            if wt is None:
+                wt = packed_weight(w)               # [k3, cout, cin]: K-major B operand
+            wt = wt.contiguous()
             rc = L.cvb200_sc_conv_forward_tc(_ptr(x), x.shape[0], cin, _ptr(wt), cout, _ptr(table), n_out, k3,
                                              _ptr(b) if b is not None else None, _ptr(out), _stream())
             _lib.check(rc, "cvb200_sc_conv_forward_tc")
         else:
+            w = w.contiguous() if w is not None else wt.transpose(1, 2).contiguous()
             rc = L.cvb200_sc_conv_forward(_ptr(x), cin, _ptr(w), cout, _ptr(table), n_out, k3,
                                           _ptr(b) if b is not None else None, _ptr(out), _stream())
             _lib.check(rc, "cvb200_sc_conv_forward")
@@ -67,7 +112,7 @@ def conv_wgrad(a, b, table, table_on_b=False, mode=None):
     n_rows, k3 = table.shape
     a, b = a.contiguous(), b.contiguous()
     dw = torch.empty((k3, a.shape[1], b.shape[1]), dtype=torch.float32, device=a.device)
-    mode = mode or _FORWARD_MODE
+    mode = resolve_mode(mode)
     ca, cb = a.shape[1], b.shape[1]
     with torch.cuda.device(a.device):
         if mode == "tf32" and not table_on_b and ca % 32 == 0 and cb % 32 == 0 and cb <= 256:
@@ -105,11 +150,12 @@ def _im2col_width(k3, cin):
 
 class SparseConvFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, table, table_t, kind):
+    def forward(ctx, x, w, bias, table, table_t, kind, mode):
         ctx.table, ctx.table_t, ctx.kind, ctx.has_bias = table, table_t, kind, bias is not None
         cin, cout = w.shape[1], w.shape[2]
         ctx.im2col = None
-        if _FORWARD_MODE == "tf32" and cin % 32 != 0 and cin <= 8 and cout % 32 == 0 and cout <= 256 and not ctx.needs_input_grad[0]:
+        ctx.mode = mode                        # decided by the caller: inside a Function autograd is always off
+        if mode == "tf32" and cin % 32 != 0 and cin <= 8 and cout % 32 == 0 and cout <= 256 and not ctx.needs_input_grad[0]:
             # small input width: im2col + one tensor-core product (forward) / one tensor-core weight gradient (backward)
             k3 = w.shape[0]
             width = _im2col_width(k3, cin)
@@ -119,9 +165,9 @@ class SparseConvFunction(torch.autograd.Function):
             ident = torch.arange(col.shape[0], dtype=torch.int32, device=x.device).view(-1, 1)
             ctx.im2col = (col, ident, k3, cin)
             ctx.save_for_backward(x, w)
-            return conv_table_forward(col, wp, ident, bias)
+            return conv_table_forward(col, wp, ident, bias, mode=mode)
         ctx.save_for_backward(x, w)
-        return conv_table_forward(x, w, table, bias)
+        return conv_table_forward(x, w, table, bias, mode=mode)
 
     @staticmethod
     def backward(ctx, gout):
@@ -129,20 +175,24 @@ class SparseConvFunction(torch.autograd.Function):
         gout = gout.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            if ctx.kind == "same":
-                wt = w.flip(0).transpose(1, 2).contiguous()
+            # gx[i] = sum_k gout[table_t[i,k]] @ W[k]^T: the B operand [K3, cin, cout] of that product is the kernel as stored; a
+            # centred odd kernel's transposed map is the map itself with the offsets mirrored
+            cin, cout, k3 = w.shape[1], w.shape[2], w.shape[0]
+            if ctx.mode == "tf32" and _tc_ok(cout, cin, k3):
+                tab = mirrored_table(ctx.table_t) if ctx.kind == "same" else ctx.table_t
+                gx = conv_table_forward(gout, None, tab, mode="tf32", wt=w.detach())
             else:
-                wt = w.transpose(1, 2).contiguous()
-            gx = conv_table_forward(gout, wt, ctx.table_t)
+                wt = (w.flip(0) if ctx.kind == "same" else w).transpose(1, 2).contiguous()
+                gx = conv_table_forward(gout, wt, ctx.table_t, mode=ctx.mode)
         if ctx.needs_input_grad[1] and ctx.im2col is not None:
             col, ident, k3, cin = ctx.im2col
-            gw = conv_wgrad(col, gout, ident)[0, :k3 * cin].reshape(k3, cin, gout.shape[1])
+            gw = conv_wgrad(col, gout, ident, mode=ctx.mode)[0, :k3 * cin].reshape(k3, cin, gout.shape[1])
         elif ctx.needs_input_grad[1]:
-            gw = conv_wgrad(x, gout, ctx.table)
+            gw = conv_wgrad(x, gout, ctx.table, mode=ctx.mode)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.sum(0, keepdim=True)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
 def sparse_conv(x, w, bias, table, table_t, kind):
-    return SparseConvFunction.apply(x, w, bias, table, table_t, kind)
+    return SparseConvFunction.apply(x, w, bias, table, table_t, kind, resolve_mode())

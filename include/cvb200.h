@@ -50,19 +50,12 @@ size_t cvb200_hv_grid_dims_work_bytes(void);
 int cvb200_hv_grid_dims(const float *d_points, int64_t n, float res, void *d_work,
                         float *h_corner, float *h_maxpt, int32_t *h_dims, void *stream);
 
-/* Bytes of the device workspace of cvb200_hv_forward for n points, num_rots rotations and a grid of dims[0..2] voxels:
- * three uint32 arrays over the 8x8x8-voxel tiles of the grid (counts, offsets, fill cursors) + one 4-byte record per
- * (vote, touched tile) -- a vote's 2x2x2 footprint touches at most 8 tiles, hence 32 n num_rots bytes of records.
- * CONTRACT: the tile counters (the first 4 * ceil(X/8) ceil(Y/8) ceil(Z/8) bytes) and the ticket word behind the three arrays
- * must be zero when cvb200_hv_forward is entered and are zero again when the call's work completes, so a caller
- * zero-fills the workspace once after allocation and may then reuse it forever on the same stream (also for other grid
- * sizes only after zero-filling it again).  16-byte alignment required. */
-size_t cvb200_hv_forward_work_bytes_n(const int32_t dims[3], int64_t n, int32_t num_rots);
-
-/* Measurement aid: 0 selects the round-1 forward (vector reductions into an interleaved [G][8] float workspace of
- * cvb200_hv_forward_work_bytes(dims) bytes + write-out pass), 1 (default) the sorted-tile forward. */
+/* Bytes of the device workspace of cvb200_hv_forward for a grid of dims[0..2] voxels:
+ * an interleaved accumulator of 8 floats (one 32-byte sector) per voxel.
+ * CONTRACT: the workspace must be all-zero when cvb200_hv_forward is entered and is
+ * all-zero again when the call's work completes (the write-out pass re-zeroes it), so a caller zero-fills it once after allocation and may
+ * then reuse it forever on the same stream.  16-byte alignment required. */
 size_t cvb200_hv_forward_work_bytes(const int32_t dims[3]);
-int cvb200_hv_set_impl(int32_t impl);
 
 /* hv_cuda.forward (houghvoting/src/hv_cuda.cpp:30-45 -> hv_cuda_kernel.cu:121-165):
  * scatter every point's num_rots oriented centre votes into the grid with trilinear
@@ -73,7 +66,7 @@ int cvb200_hv_set_impl(int32_t impl);
  *   d_grid_obj [X,Y,Z], d_grid_rot [X,Y,Z,2], d_grid_scale [X,Y,Z,3]: outputs, every
  *       element is written exactly once (no pre-zeroing needed; the reference needs 3
  *       memsets)
- *   d_work / work_bytes    see cvb200_hv_forward_work_bytes_n; n * num_rots must be below 2^32 */
+ *   d_work / work_bytes    see cvb200_hv_forward_work_bytes */
 int cvb200_hv_forward(const float *d_points, const float *d_xyz, const float *d_scale, const float *d_obj,
                       int64_t n, float res, int32_t num_rots, const float corner[3], const int32_t dims[3],
                       float *d_grid_obj, float *d_grid_rot, float *d_grid_scale,

@@ -35,3 +35,13 @@ def lib_built():
     """Build (if stale) and return the path of the C-ABI library; CPU-only, no compute."""
     from canonicalvoting_b200 import build
     return build.build()
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_unless_a_test_says_otherwise():
+    """The parity tests compare the module path with the oracle at fp32 accuracy: pin the exact-fp32 convolution for every test
+    (the library default is 'auto': tensor cores wherever autograd is off).  Tests of the tensor-core path select it themselves."""
+    from canonicalvoting_b200.sparse import functional
+    functional.set_forward_mode("fp32")
+    yield
+    functional.set_forward_mode("fp32")

@@ -32,8 +32,8 @@ def test_python_binding_covers_header(lib_built):
     assert L.cvb200_abi_version() == _lib.ABI_VERSION
     assert L.cvb200_hv_grid_dims_work_bytes() >= 128
     dims = (ctypes.c_int32 * 3)(128, 128, 128)
-    wb = L.cvb200_hv_forward_work_bytes_n(dims, 50000, 12)
-    assert wb == 4 * ((3 * 16 ** 3 + 2 + 3) // 4 * 4 + 8 * 50000 * 12)        # tile arrays + one record per (vote, touched tile)
+    wb = L.cvb200_hv_forward_work_bytes(dims)
+    assert wb == 128 ** 3 * 32
 
 
 def test_argument_errors_do_not_need_a_gpu(lib_built):

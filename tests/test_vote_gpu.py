@@ -156,8 +156,8 @@ def test_full_size_properties_C5():
         go3, gr3, gs3 = hv_cuda.forward(p, x, s, o, res_t, rots_t)
         assert_grid_close(go3.cpu().numpy(), go.cpu().numpy(), what="idempotence obj")
         assert_grid_close(gs3.cpu().numpy(), gs.cpu().numpy(), what="idempotence scale")
-    for w, _ in H._work_cache.values():
-        assert not w[:4 * 32 ** 3].any(), "tile counters not re-zeroed"
+    for w in H._work_cache.values():
+        assert not w.any(), "workspace not re-zeroed"
 
 
 def test_edge_cases():

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tools/time_vote.py -- the vote op alone (hv_cuda.forward_host, geometry known): CUDA events per call, L2 flushed or warm,
-sorted-tile forward vs the round-1 reduction forward (GPU box)."""
+(GPU box)."""
 import json
 import sys
 
@@ -17,8 +17,7 @@ for wl in ("C2", "C5") + (("R120",) if "all" in sys.argv else ()):
     res, R = sc["res"], sc["num_rots"]
     corner, _, dims = H.grid_dims(p, res)
     nbytes = 40 * len(sc["points"]) + 24 * dims[0] * dims[1] * dims[2]
-    for impl in (1, 0):
-        H.set_impl(bool(impl))
+    for impl in (0,):
         for cold in (True, False):
             ts = []
             for it in range(13):
@@ -32,8 +31,7 @@ for wl in ("C2", "C5") + (("R120",) if "all" in sys.argv else ()):
                 if it >= 3:
                     ts.append(a.elapsed_time(b) * 1e3)
             ts.sort()
-            key = "%s impl=%s %s" % (wl, "tiles" if impl else "red", "L2 cold" if cold else "L2 warm")
+            key = "%s %s" % (wl, "L2 cold" if cold else "L2 warm")
             out[key] = {"median_us": ts[len(ts) // 2], "min_us": ts[0], "GBps": nbytes / ts[len(ts) // 2] / 1e3}
             print("%-28s median %8.1f us  min %8.1f us  -> %7.0f GB/s of 40N+24G" % (key, ts[len(ts) // 2], ts[0], nbytes / ts[len(ts) // 2] / 1e3), flush=True)
-H.set_impl(True)
 json.dump(out, open("gpurun_out/time_vote.json", "w"), indent=1)
