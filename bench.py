@@ -301,10 +301,10 @@ def main():
     from canonicalvoting_b200.engine import MinkUNetEngine
     from canonicalvoting_b200.hough_voting import back_project
 
-    if os.environ.get("CVB200_CONV_OPTS"):      # A/B switch for measurements: "<allow_split>,<use_pdl>"
-        from canonicalvoting_b200 import _lib
+    if os.environ.get("CVB200_CONV_OPTS"):      # A/B switch for measurements: "<allow_split>,<launch bits>"
+        from canonicalvoting_b200 import engine as _engine
         o = [int(x) for x in os.environ["CVB200_CONV_OPTS"].split(",")]
-        _lib.load().cvb200_sc_set_conv_options(o[0], o[1])
+        _engine.set_conv_options(o[0], o[1])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

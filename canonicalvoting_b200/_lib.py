@@ -75,11 +75,17 @@ SIGNATURES.update({
 
 
 
+class DecodeArgs(ctypes.Structure):
+    """cvb200_decode_args (include/cvb200.h)."""
+    _fields_ = [("xyz", _vp), ("scale", _vp), ("class_pred", _vp), ("prob", _vp), ("coords", _vp), ("points", _vp),
+                ("res", ctypes.c_float), ("nclasses", _i32), ("log_scale", _i32)]
+
+
 class ScOp(ctypes.Structure):
     """cvb200_sc_op (include/cvb200.h)."""
     _fields_ = [("kind", _i32), ("cin", _i32), ("cout", _i32), ("k3", _i32), ("ldi", _i32), ("ldo", _i32), ("ldr", _i32),
                 ("relu", _i32), ("n_out", _i64), ("n_in", _i64), ("in_", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("table", _vp),
-                ("out", _vp), ("n_out_dev", _vp)]
+                ("out", _vp), ("n_out_dev", _vp), ("decode", ctypes.POINTER(DecodeArgs))]
 
 
 class MapsLayout(ctypes.Structure):
@@ -100,6 +106,14 @@ SIGNATURES.update({
     "cvb200_sc_run_program": (ctypes.c_int, [ctypes.POINTER(ScOp), _i32, _vp]),
     "cvb200_head_decode": (ctypes.c_int, [_f, _i32, _i64, _i32, _i32, _f, _f, _vp, _f, _vp]),
     "cvb200_head_decode_points": (ctypes.c_int, [_f, _i32, _i64, _i32, _i32, _f, _f, _vp, _f, _vp, ctypes.c_float, _f, _vp]),
+})
+
+SIGNATURES.update({
+    "cvb200_graph_begin": (ctypes.c_int, [_vp]),
+    "cvb200_graph_end": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i64)]),
+    "cvb200_graph_abort": (ctypes.c_int, [_vp]),
+    "cvb200_graph_launch": (ctypes.c_int, [_vp, _vp]),
+    "cvb200_graph_destroy": (ctypes.c_int, [_vp]),
 })
 
 _lib = None

@@ -68,6 +68,7 @@ struct PsPlan {
     int dbg;          // measurement aid (cvb200_sc_set_conv_debug): 1 no gather copies, 2 no zero-fill copies, 4 no MMA, 8 no weight TMA
     int allow_split;  // 0: never cut tiles into pieces
     int force_ks;     // probe override of ks (0 = planner's choice)
+    int lean;         // 1: producer-side proxy fence + one MMA issuer (see the gather role); 0: asynchronous arrivals + two issuers
 };
 
 struct PsHeader {
@@ -106,6 +107,15 @@ __host__ __device__ inline void ps_plan_rows(long long n_out, int slots, PsPlan 
     }
     P->n_units = P->n_whole + (P->n_tiles - P->n_whole) * P->ks;
 }
+
+// fused head decode (cvb200_decode_args) as the kernel sees it; xyz == nullptr: off
+struct PsDecode {
+    float *xyz, *scale, *prob, *points;
+    long long *cls;
+    const int4 *coords;
+    float res;
+    int log_scale;
+};
 
 struct PsUnit {
     int row0, n0, kb0, kb1, pieces, split_tile;
@@ -157,7 +167,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias,
                        const float *__restrict__ residual, int ldr, int relu, float *__restrict__ out, int ldo, const PsPlan P0,
                        float *__restrict__ scratch, int *__restrict__ counters, long long *__restrict__ trace, int g4,
-                       const int *__restrict__ n_out_dev) {
+                       const int *__restrict__ n_out_dev, const PsDecode dec) {
     extern __shared__ __align__(1024) unsigned char smem[];
     PsHeader &H = *reinterpret_cast<PsHeader *>(smem);
     unsigned char *stage0 = smem + 1024 + 16384;       // [header 1 KiB][epilogue staging 4 x 4 KiB][ring]
@@ -169,11 +179,11 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
 
     if (tid == 0) {
         for (int s = 0; s < P0.stages; s++) {
-            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), 1 + 32);
+            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), P0.lean ? 1 + 1 : 1 + 32);
             tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
-            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), PS_DBG(P0, 0x40000) ? 1 : 2);      // both MMA warps
+            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), (P0.lean || PS_DBG(P0, 0x40000)) ? 1 : 2);      // both MMA warps
             tm_mbar_init(tm_smem_u32(&H.acc_empty[b]), 4);
             tm_mbar_init(tm_smem_u32(&H.turn[b]), 1);
         }
@@ -247,7 +257,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // order, stages are released in order, and the first k-block of a unit overwrites the accumulator before anything
         // is added to it.  Both warps commit to acc_full (count 2).
         const int me = warp == 4 ? 0 : 1;
-        const int issuers = PS_DBG(P, 0x40000) ? 1 : 2;            // measurement aid: one issuer only (warp 12 idles)
+        const int issuers = (P.lean || PS_DBG(P, 0x40000)) ? 1 : 2;   // lean protocol: one issuer (warp 12 idles)
         int li = 0, n_base = 0;
         for (int u = blockIdx.x; u < P.n_units && me < issuers; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
@@ -267,7 +277,9 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 if (tr && me == 0 && lane == 0 && tn < 256) { trace[3 * tn] = t0; trace[3 * tn + 1] = clock64(); }
                 const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
                 const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
-                if (!PS_DBG(P, 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> tensor core
+                // cp.async wrote through the generic proxy, the tensor core reads through the async proxy: fence here, unless the
+                // producers already did before arriving (lean protocol)
+                if (!P.lean && !PS_DBG(P, 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 // my turn: the other warp has issued k-block n - 1
                 if (n > 0 && issuers == 2) tm_mbar_wait(tm_smem_u32(&H.turn[me]), (uint32_t)(((n >> 1) + me + 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -302,7 +314,11 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // warp placement: a scheduler (warp % 4) that hosts an MMA issuer or the TMA warp hosts no gather warp, whose long
         // instruction streams would delay the issuers' latency-critical hand-shakes
         const int w = warp < 4 ? warp - 1 : warp - 2, c = lane & 7, rb = lane >> 3;   // warps 1,2,3,5,6,7 -> 0..5
-        const int W = P.stages < kPsProducers ? P.stages : kPsProducers;   // producing warps: own k-blocks must be less than a ring apart
+        // producing warps: own k-blocks must be less than a ring apart (lean: strictly less than the ring minus the one k-block a
+        // warp's arrival lags behind, or the arrival would wait for its own consumption)
+        const int Wmax = P.lean ? P.stages - 1 : P.stages;
+        const int W = Wmax < kPsProducers ? Wmax : kPsProducers;
+        uint32_t pend_bar = 0;                                             // lean: full barrier of my k-block whose copies are in flight
         const uint32_t off_even = (uint32_t)(rb * 128 + ((c ^ rb) << 4)), off_odd = (uint32_t)((rb + 4) * 128 + ((c ^ (rb + 4)) << 4));
         const size_t ld4 = (size_t)ldi;
         int n_base = 0;
@@ -373,12 +389,39 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(id >= 0 ? 16u : 0u) : "memory");
                 }
                 }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
+                if (P.lean) {
+                    // Lean protocol: the copies of this k-block form a group; the warp completes its PREVIOUS k-block -- waits for
+                    // that group, makes the data visible to the async proxy (fence.proxy.async, here instead of on the MMA
+                    // issuer's critical path) and arrives once -- so two of its k-blocks are always in flight.
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (pend_bar) {
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pend_bar) : "memory");
+                        }
+                    }
+                    pend_bar = tm_smem_u32(&H.full_bar[s]);
+                } else {
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
+                }
                 if (tr && tid == 32 && tn < 256) { trace[768 + 3 * tn + 2] = clock64(); }
                 tn++;
             }
             (void)k_nxt;
             n_base += U.kb1 - U.kb0;
+            // lean: the unit's last k-block of this warp must not wait for the next unit (its first k-block may belong to a tile this
+            // CTA only reaches after the epilogue freed an accumulator)
+            if (pend_bar) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pend_bar) : "memory");
+                }
+                pend_bar = 0;
+            }
         }
     } else {
         // ===== epilogue warps 8..11: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
@@ -428,7 +471,62 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 if (tr && et == 0 && li == 0) trace[3 * 768 + 5] = clock64();
                 finish = H.last_flag != 0;
             }
-            if (finish && (P.nc & 31) == 0) {
+            if (dec.xyz != nullptr) {
+                // ===== fused head decode of the joint model (eval_joint.py:173-193, 9 classes: 64 columns = xyz[9][3] | scale[9][3] |
+                // logits[10]): the row never leaves the SM.  Same operations in the same order as head_decode_kernel
+                // (sparse_engine.cu), on the accumulator columns + bias.  The launcher guarantees whole tiles (no pieces), nc == 64.
+                uint32_t t3[16];
+                ps_tmem_ld16(taddr0 + 48u, t3);                           // columns 48..63: scale of classes 7, 8 and the 10 logits
+                float lg[10];
+#pragma unroll
+                for (int c = 0; c < 10; c++) lg[c] = __uint_as_float(t3[6 + c]) + (bias ? __ldg(bias + 54 + c) : 0.f);
+                float best = -INFINITY, best_obj = -INFINITY;
+                int k = 0, k_obj = 0;
+#pragma unroll
+                for (int c = 0; c < 10; c++) {                            // first maximum, like torch.argmax
+                    if (lg[c] > best) { best = lg[c]; k = c; }
+                    if (c < 9 && lg[c] > best_obj) { best_obj = lg[c]; k_obj = c; }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 10; c++) sum += expf(lg[c] - best);
+                if (k == 9) k = 0;                                        // class_label_idx[class_label_idx == nclasses] = 0  (:178)
+                float px[3] = {0.f, 0.f, 0.f}, ps[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int cb = 0; cb < 4; cb++) {
+                    uint32_t t[16];
+                    if (cb < 3) ps_tmem_ld16(taddr0 + (uint32_t)(cb * 16), t);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int col = cb * 16 + j;
+                        if (col >= 54) continue;
+                        const float v = __uint_as_float(cb < 3 ? t[j] : t3[j]) + (bias ? __ldg(bias + col) : 0.f);
+#pragma unroll
+                        for (int e = 0; e < 3; e++) {
+                            if (col == 3 * k + e) px[e] = v;
+                            if (col == 27 + 3 * k + e) ps[e] = v;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem_u32(&H.acc_empty[buf])) : "memory");
+                if (r < n_out) {
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        dec.xyz[3 * (size_t)r + e] = px[e];
+                        dec.scale[3 * (size_t)r + e] = dec.log_scale ? expf(ps[e]) : ps[e];
+                    }
+                    dec.cls[r] = k_obj;                                   // argmax over the object classes          (:188)
+                    dec.prob[r] = expf(best_obj - best) / sum;            // max softmax over the object classes     (:189)
+                    if (dec.coords) {
+                        const int4 c = __ldg(dec.coords + r);
+                        dec.points[3 * (size_t)r] = __fmul_rn((float)c.y, dec.res);
+                        dec.points[3 * (size_t)r + 1] = __fmul_rn((float)c.z, dec.res);
+                        dec.points[3 * (size_t)r + 2] = __fmul_rn((float)c.w, dec.res);
+                    }
+                }
+            } else if (finish && (P.nc & 31) == 0) {
                 // Coalesced write-out: 32-column chunks go through a swizzled per-warp staging tile, so that a warp
                 // instruction stores (and reads the residual of) 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
                 // (The uncoalesced version kept so many sectors in flight that the MMA warp's proxy fence -- a MEMBAR --
@@ -552,6 +650,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
 }
 
 // ---------------------------------------------------------------------------------------------------------- host side
+int g_ps_lean = 0;
 int g_ps_allow_split = 1;   // 0: never cut tiles into pieces (bit-reproducible summation order; used by the tests)
 int g_ps_use_pdl = 1;
 int g_ps_debug = 0;
@@ -597,6 +696,7 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ct
     // layers) and are no longer offered; the register budget is now spent on one CTA
     *ctas_per_sm = 1;
     P->allow_split = g_ps_allow_split;
+    P->lean = g_ps_lean;
     P->force_ks = (g_ps_debug >> 8) & 255;
     ps_plan_rows(n_out, kNumSMs * *ctas_per_sm, P);
     int stages = (kPsSmemBytes - 1024 - 16384) / stage_bytes;
@@ -612,20 +712,34 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ct
 // K = 32 * ceil(g4 / 8) = (neighbour, channel) pairs; cin must be that K, k3 must be 1, d_wt = [cout][K]
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
-                        cudaStream_t stream, int g4, const int32_t *d_n_out) {
+                        cudaStream_t stream, int g4, const int32_t *d_n_out, const cvb200_decode_args *decode) {
     CVB_REQUIRE(g4 == 0 || (k3 == 1 && ldi == 4 && cin == 32 * ((g4 + 7) / 8)), CVB200_EINVAL,
                 "sc_conv (4-channel gather): needs k3 == 1, ldi == 4, cin == 32 * ceil(width / 8) (got %d, %d, %d for width %d)", k3, ldi, cin, g4);
     CVB_REQUIRE(cin > 0 && cin % kPsKB == 0 && cout >= 16 && cout <= 1024 && cout % 16 == 0 && k3 > 0, CVB200_EINVAL,
                 "sc_conv_forward_tc: needs cin %% 32 == 0, cout %% 16 == 0, 16 <= cout (got %d, %d, %d)", cin, cout, k3);
     CVB_REQUIRE(n_out >= 0 && n_out < (1LL << 31) && n_in > 0 && n_in < (1LL << 31), CVB200_EINVAL, "sc_conv_forward_tc: bad n_out / n_in");
     if (n_out == 0) return 0;
-    CVB_REQUIRE(d_in && d_wt && d_nbr && d_out, CVB200_EINVAL, "sc_conv_forward_tc: NULL argument");
+    CVB_REQUIRE(d_in && d_wt && d_nbr && (d_out || decode), CVB200_EINVAL, "sc_conv_forward_tc: NULL argument");
     CVB_REQUIRE(((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_wt) | reinterpret_cast<uintptr_t>(d_out) |
                   reinterpret_cast<uintptr_t>(d_res)) & 15) == 0 && ldi % 4 == 0 && ldo % 4 == 0 && ldr % 4 == 0,
                 CVB200_EINVAL, "sc_conv_forward_tc: 16-byte aligned pointers and row strides required");
+    PsDecode dec = {};
+    if (decode) {
+        CVB_REQUIRE(decode->nclasses == 9 && cout == 64 && !d_res && !relu, CVB200_EINVAL,
+                    "sc_conv (fused decode): needs the joint head (9 classes, 64 output channels), no residual, no ReLU (got %d classes, %d channels)",
+                    decode->nclasses, cout);
+        CVB_REQUIRE(decode->xyz && decode->scale && decode->class_pred && decode->prob && (decode->coords == nullptr) == (decode->points == nullptr),
+                    CVB200_EINVAL, "sc_conv (fused decode): NULL output (coords and points go together)");
+        dec.xyz = decode->xyz; dec.scale = decode->scale; dec.prob = decode->prob; dec.points = decode->points;
+        dec.cls = (long long *)decode->class_pred; dec.coords = (const int4 *)decode->coords; dec.res = decode->res;
+        dec.log_scale = decode->log_scale;
+    }
     PsPlan P;
     int ctas_per_sm = 1;
+    const int keep_split = g_ps_allow_split;
+    if (decode) g_ps_allow_split = 0;        // the decode epilogue works on whole tiles (a 1x1x1 convolution has 3 k-blocks: nothing to cut)
     ps_plan(n_out, cin, cout, k3, &P, &ctas_per_sm);
+    g_ps_allow_split = keep_split;
     PsWorkspace ws;
     if (int rc = ps_workspace(stream, &ws)) return rc;
     alignas(64) CUtensorMap map_b;
@@ -649,7 +763,7 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
     cfg.attrs = attr;
     cfg.numAttrs = g_ps_use_pdl ? 1 : 0;
     CVB_CUDA(cudaLaunchKernelEx(&cfg, sc_conv_persist_kernel, map_b, d_in, ldi, cout, (const int *)d_nbr, (int)n_out, k3, d_bias, d_res,
-                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace, g4, (const int *)d_n_out));
+                                ldr, relu, d_out, ldo, P, ws.scratch, ws.counters, g_ps_trace, g4, (const int *)d_n_out, dec));
     return 0;
 }
 
@@ -659,12 +773,13 @@ extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_
                                          const int32_t *d_nbr, int64_t n_out, int32_t k3, const float *d_bias, float *d_out,
                                          void *stream_) {
     return cvb200::launch_conv_persist(d_in, n_in, cin, cin, d_wt, cout, d_nbr, n_out, k3, d_bias, nullptr, 0, 0, d_out, cout,
-                                       (cudaStream_t)stream_, 0, nullptr);
+                                       (cudaStream_t)stream_, 0, nullptr, nullptr);
 }
 
 extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) {
     cvb200::g_ps_allow_split = allow_split != 0;
-    cvb200::g_ps_use_pdl = use_pdl != 0;
+    cvb200::g_ps_use_pdl = (use_pdl & 1) != 0;
+    cvb200::g_ps_lean = (use_pdl & 2) != 0;            // measurement: bit 1 selects the lean producer / issuer protocol
     return 0;
 }
 

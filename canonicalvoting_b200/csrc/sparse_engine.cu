@@ -13,7 +13,7 @@ namespace cvb200 {
 
 int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const float *d_wt, int cout, const int32_t *d_nbr,
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
-                        cudaStream_t stream, int g4, const int32_t *d_n_out);
+                        cudaStream_t stream, int g4, const int32_t *d_n_out, const cvb200_decode_args *decode = nullptr);
 
 // Convolution with a tiny input width (the 3-channel 5^3 stem, utils/minkunet.py:53): one warp per output row, the
 // whole kernel (K^3 x cin x cout) in shared memory, lanes = output channels; neighbour ids are read 32 at a time and
@@ -120,10 +120,10 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
         const cvb200_sc_op &o = ops[i];
         if (o.kind == CVB200_OP_CONV_TC) {
             const int rc = launch_conv_persist(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr,
-                                               o.relu, o.out, o.ldo, stream, 0, o.n_out_dev);
+                                               o.relu, o.out, o.ldo, stream, 0, o.n_out_dev, o.decode);
             if (rc) return rc;
         } else if (o.kind == CVB200_OP_CONV_SMALLCIN) {
-            CVB_REQUIRE(!o.n_out_dev, CVB200_EINVAL, "sc_run_program: op %d: a device-side row count needs a tensor-core kind", i);
+            CVB_REQUIRE(!o.n_out_dev && !o.decode, CVB200_EINVAL, "sc_run_program: op %d: a device-side row count / fused decode needs a tensor-core kind", i);
             CVB_REQUIRE(o.cin >= 1 && o.cin <= 8 && o.cout % 32 == 0 && o.cout <= 128 && !o.residual, CVB200_EINVAL,
                         "sc_run_program: op %d: small-cin convolution needs cin <= 8, cout in {32,64,96,128}, no residual", i);
             const size_t smem = sizeof(float) * (size_t)o.k3 * o.cin * o.cout;

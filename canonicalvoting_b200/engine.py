@@ -26,16 +26,25 @@ compat package) into a flat program of fused convolution ops executed back to ba
 import collections
 import ctypes
 import os
+import threading
 
 import torch
 
 from . import _lib
 from .sparse.coords import CoordinateManager, _ptr, _stream
 
+CONV_OPTIONS = [1, 1]      # (allow_split, launch bits) the library runs with: set_conv_options() keeps it in step
+
 _ENCODER = [("conv1p1s2", "bn1", "block1"), ("conv2p2s2", "bn2", "block2"), ("conv3p4s2", "bn3", "block3"),
             ("conv4p8s2", "bn4", "block4")]
 _DECODER = [("convtr4p16s2", "bntr4", "block5"), ("convtr5p8s2", "bntr5", "block6"), ("convtr6p4s2", "bntr6", "block7"),
             ("convtr7p2s2", "bntr7", "block8")]
+
+
+def set_conv_options(allow_split=1, launch_bits=1):
+    """cvb200_sc_set_conv_options for the whole process (measurement switch; the SceneGraph capture restores these values)."""
+    CONV_OPTIONS[0], CONV_OPTIONS[1] = int(allow_split), int(launch_bits)
+    _lib.load().cvb200_sc_set_conv_options(int(allow_split), int(launch_bits))
 
 
 def _fold(conv, bn):
@@ -110,6 +119,7 @@ class MinkUNetEngine:
         self._pool = None                     # one worker thread for prefetch()
         self._pinned = None                   # count read-back buffer of the fused map builder (one build at a time)
         self._cm_building = None
+        self._maps_lock = threading.Lock()
         self.fused_maps = True                # cvb200_sc_build_maps (one sync per scene); False: step-by-step coordinate manager
         self.stem_gather4 = os.environ.get("CVB200_STEM_IM2COL", "0") != "1"   # False: stem as im2col + product (refresh() after changing)
         self.refresh()
@@ -241,9 +251,11 @@ class MinkUNetEngine:
     def build_maps(self, coords):
         """Coordinate levels + every neighbour table the network needs (device work + one scalar read per level)."""
         if self.fused_maps:
-            if self._pinned is None:
-                self._pinned = torch.empty(8, dtype=torch.int32).pin_memory()
-            return CoordinateManager.build_unet(coords, int(self.model.conv0p1s1.kernel_size), 4, self._pinned)
+            # one pinned read-back buffer per engine: builds (caller thread, prefetch worker) take turns
+            with self._maps_lock:
+                if self._pinned is None:
+                    self._pinned = torch.empty(8, dtype=torch.int32).pin_memory()
+                return CoordinateManager.build_unet(coords, int(self.model.conv0p1s1.kernel_size), 4, self._pinned)
         cm = CoordinateManager(coords)
         for ts in (1, 2, 4, 8):
             cm.down(ts)
@@ -253,8 +265,14 @@ class MinkUNetEngine:
             self._identity(cm, ts)
         return cm
 
-    def build(self, coords, feats, cm=None):
-        """Buffers + program for one batch of scenes. Returns (ops array, output tensor [N, Cout], keep-alive list)."""
+    def can_fuse_decode(self):
+        """The head decode can run in the epilogue of `final` (cvb200_decode_args): joint head with 9 classes = 64 channels."""
+        return self.nclasses == 9 and self.out_channels == 64 and self.w["final"][0].shape[1] == 64
+
+    def build(self, coords, feats, cm=None, decode=None):
+        """Buffers + program for one batch of scenes. Returns (ops array, output tensor [N, Cout], keep-alive list).
+        `decode` (_lib.DecodeArgs): the last convolution decodes its rows instead of storing them (the output tensor then
+        stays unwritten)."""
         if cm is None:
             cm = self.build_maps(coords)
         self._cm_building = cm
@@ -312,6 +330,10 @@ class MinkUNetEngine:
             x = self._blocks(ops, arena, block, cm, ts, cat[fine])
         out = arena.matrix(n[1], self.w["final"][0].shape[1])          # padded to a multiple of 16 channels
         self._op(ops, "final", x, out, self._identity(cm, 1), relu=False, out_ts=1)
+        if decode is not None:
+            if not self.can_fuse_decode():
+                raise RuntimeError("fused head decode needs the joint head: 9 classes, 64 output channels")
+            ops[-1][0].decode = ctypes.pointer(decode)
         self._cm_building = None
         buf = arena.commit()
         arr = (_lib.ScOp * len(ops))()
@@ -319,7 +341,7 @@ class MinkUNetEngine:
             o.in_, o.out = src_.ptr, dst_.ptr
             o.residual = res_.ptr if res_ is not None else None
             arr[i] = o
-        return arr, arena.tensor(out)[:, :self.out_channels], [cm, feats, buf]
+        return arr, arena.tensor(out)[:, :self.out_channels], [cm, feats, buf, decode]
 
     # ------------------------------------------------------------------ execution
     def __call__(self, coords, feats, maps=None):
@@ -395,11 +417,12 @@ class MinkUNetEngine:
         prob = torch.softmax(feats[:, 6:8], dim=-1)[:, 1].contiguous()
         return xyz, scale.contiguous(), prob
 
-    def graph_lane(self, n_voxels, vote=None):
+    def graph_lane(self, n_voxels, vote=None, fuse_decode=None):
         """A `SceneGraph` for scenes of exactly `n_voxels` voxels: persistent input / table / activation / output buffers and ONE
         captured CUDA graph holding the coordinate-map builder, the whole convolution program, the head decode (+ scan_points)
-        and -- with `vote=dict(res=, num_rots=, corner=, dims=)` -- the vote op.  See SceneGraph."""
-        return SceneGraph(self, int(n_voxels), vote)
+        and -- with `vote=dict(res=, num_rots=, corner=, dims=)` -- the vote op.  `fuse_decode` (default: whenever the head
+        allows it) runs the decode in the epilogue of the last convolution; out["feats"] is then not produced.  See SceneGraph."""
+        return SceneGraph(self, int(n_voxels), vote, self.can_fuse_decode() if fuse_decode is None else bool(fuse_decode))
 
     def predict(self, coords, feats, maps=None, res=None):
         """Network + head decode.  With `res` the tuple has a fifth element: scan_points = coords[:, 1:] * res."""
@@ -428,9 +451,9 @@ class SceneGraph:
     The returned tensors are the lane's persistent buffers: they are overwritten by the lane's next run (stream-ordered), so
     use one lane per scene in flight.  Memory is what the upper bounds cost: ~2 GB per lane at 50 000 voxels."""
 
-    def __init__(self, engine, n, vote=None):
+    def __init__(self, engine, n, vote=None, fuse_decode=False):
         from . import hv_cuda as H
-        self.engine, self.n, self.vote = engine, n, vote
+        self.engine, self.n, self.vote, self.fuse_decode = engine, n, vote, fuse_decode
         dev = engine.device
         L = _lib.load()
         with torch.cuda.device(dev):
@@ -439,28 +462,43 @@ class SceneGraph:
             pad4 = "conv0p1s1" in engine.gather4
             self.feats4 = torch.zeros((n, 4), dtype=torch.float32, device=dev) if pad4 else self.feats_in
             self.cm = CoordinateManager.static_unet(self.coords, int(engine.model.conv0p1s1.kernel_size), 4)
-            arr, out, keep = engine.build(self.coords, self.feats4, self.cm)
-            self.arr, self.out_full, self.keep = arr, out, keep
             f32 = dict(dtype=torch.float32, device=dev)
             self.xyz, self.scale = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
             self.cls, self.prob = torch.empty((n,), dtype=torch.int64, device=dev), torch.empty((n,), **f32)
             self.points = torch.empty((n, 3), **f32)
             self.res = float(vote["res"]) if vote else 0.03
+            dec = None
+            if fuse_decode:
+                dec = _lib.DecodeArgs()
+                dec.xyz, dec.scale, dec.class_pred, dec.prob = self.xyz.data_ptr(), self.scale.data_ptr(), self.cls.data_ptr(), self.prob.data_ptr()
+                dec.coords, dec.points, dec.res = self.coords.data_ptr(), self.points.data_ptr(), self.res
+                dec.nclasses, dec.log_scale = engine.nclasses, 1 if engine.log_scale else 0
+            arr, out, keep = engine.build(self.coords, self.feats4, self.cm, decode=dec)
+            self.arr, self.out_full, self.keep = arr, (None if fuse_decode else out), keep
             self.grids = None
             if vote:
                 X, Y, Z = (int(d) for d in vote["dims"])
                 self.grids = (torch.empty((X, Y, Z), **f32), torch.empty((X, Y, Z, 2), **f32), torch.empty((X, Y, Z, 3), **f32))
             self.stream = torch.cuda.Stream(dev)
+            # The map builder runs on a high-priority branch of the graph: with several scenes in flight its small kernels are
+            # then dispatched beside the persistent convolution CTAs of another scene (they need no shared memory and few
+            # registers) instead of queueing behind that scene's pending, programmatically launched convolutions.
+            self.side = torch.cuda.Stream(dev, priority=-1)
 
             def body():
+                cur = torch.cuda.current_stream()
                 if pad4:
                     self.feats4[:, :self.feats_in.shape[1]].copy_(self.feats_in)
-                self.cm.enqueue()
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    self.cm.enqueue()
+                cur.wait_stream(self.side)
                 _lib.check(L.cvb200_sc_run_program(arr, len(arr), _stream()), "cvb200_sc_run_program")
-                rc = L.cvb200_head_decode_points(_ptr(out), out.stride(0), n, engine.nclasses, 1 if engine.log_scale else 0, _ptr(self.xyz),
-                                                 _ptr(self.scale), _ptr(self.cls), _ptr(self.prob), _ptr(self.coords),
-                                                 ctypes.c_float(self.res), _ptr(self.points), _stream())
-                _lib.check(rc, "cvb200_head_decode_points")
+                if not fuse_decode:
+                    rc = L.cvb200_head_decode_points(_ptr(out), out.stride(0), n, engine.nclasses, 1 if engine.log_scale else 0, _ptr(self.xyz),
+                                                     _ptr(self.scale), _ptr(self.cls), _ptr(self.prob), _ptr(self.coords),
+                                                     ctypes.c_float(self.res), _ptr(self.points), _stream())
+                    _lib.check(rc, "cvb200_head_decode_points")
                 if vote:
                     work = H._workspace(L, vote["dims"], dev)
                     rc = L.cvb200_hv_forward(_ptr(self.points), _ptr(self.xyz), _ptr(self.scale), _ptr(self.prob), n, self.res,
@@ -472,24 +510,32 @@ class SceneGraph:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 body()
-            self.stream.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            self.pdl = True
-            try:
-                with torch.cuda.graph(self.graph, stream=self.stream):
-                    body()
-            except Exception:
-                # a driver that cannot capture programmatic dependent launches: capture plain stream-ordered launches instead
-                torch.cuda.synchronize()
-                self.pdl = False
-                L.cvb200_sc_set_conv_options(1, 0)
+            torch.cuda.synchronize(dev)
+            self.exec, self.pdl, self.nodes = None, True, 0
+            for use_pdl in (1, 0):
+                # a driver that cannot capture programmatic dependent launches gets plain stream-ordered launches
+                L.cvb200_sc_set_conv_options(CONV_OPTIONS[0], (CONV_OPTIONS[1] & ~1) | use_pdl)
                 try:
-                    self.graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self.graph, stream=self.stream):
-                        body()
+                    with torch.cuda.stream(self.stream):
+                        sp = ctypes.c_void_p(self.stream.cuda_stream)
+                        _lib.check(L.cvb200_graph_begin(sp), "cvb200_graph_begin")
+                        try:
+                            body()
+                        except Exception:
+                            L.cvb200_graph_abort(sp)
+                            raise
+                        ex, nn = ctypes.c_void_p(), ctypes.c_int64()
+                        prio = 0 if os.environ.get("CVB200_GRAPH_NO_PRIORITY") == "1" else 1      # A/B switch for measurements
+                        _lib.check(L.cvb200_graph_end(sp, prio, ctypes.byref(ex), ctypes.byref(nn)), "cvb200_graph_end")
+                    self.exec, self.pdl, self.nodes = ex, bool(use_pdl), int(nn.value)
+                    break
+                except Exception:
+                    if not use_pdl:
+                        raise
+                    torch.cuda.synchronize(dev)
                 finally:
-                    L.cvb200_sc_set_conv_options(1, 1)
-        self.launches = len(arr) + 29 + 1 + (1 if pad4 else 0) + (2 if vote else 0)
+                    L.cvb200_sc_set_conv_options(*CONV_OPTIONS)
+        self.launches = len(arr) + 29 + (0 if fuse_decode else 1) + (1 if pad4 else 0) + (2 if vote else 0)
 
     def run(self, coords, feats):
         """Copy one scene's inputs (int32 [n,4] coordinates, float32 [n,C] features; pinned host or device tensors) into the
@@ -498,9 +544,16 @@ class SceneGraph:
             raise RuntimeError("SceneGraph built for %d voxels, got %d" % (self.n, coords.shape[0]))
         self.coords.copy_(coords, non_blocking=True)
         self.feats_in.copy_(feats, non_blocking=True)
-        self.graph.replay()
+        _lib.check(_lib.load().cvb200_graph_launch(self.exec, _stream()), "cvb200_graph_launch")
         return {"feats": self.out_full, "xyz": self.xyz, "scale": self.scale, "class_pred": self.cls, "prob": self.prob,
                 "points": self.points, "grids": self.grids}
+
+    def __del__(self):
+        try:
+            if getattr(self, "exec", None):
+                _lib.load().cvb200_graph_destroy(self.exec)
+        except Exception:
+            pass
 
     def level_counts(self):
         """Voxels per level of the lane's last scene (synchronises; diagnostics / tests)."""

@@ -55,6 +55,7 @@ class CoordinateManager:
         if not coords.is_cuda:
             raise RuntimeError("canonicalvoting_b200.sparse needs CUDA coordinates (there is no CPU path)")
         self.device = coords.device
+        self._validate(coords)
         self.levels = {1: Level(coords.contiguous(), 1)}
         self._nbr = {}      # (tensor_stride, ksize) -> [n, ksize^3] int32
         self._down = {}     # fine tensor_stride -> dict(children, up_table, parent, koff)
@@ -62,6 +63,21 @@ class CoordinateManager:
         # stride-2 levels, their 3^3 maps, children / parent tables) with one host synchronisation, instead of a read-back per
         # level; whatever a network asks beyond that is still built step by step on the same hash tables.
         self._lazy_unet = not torch.is_grad_enabled()
+
+    @staticmethod
+    def _validate(coords):
+        """The hash keys pack (batch, x, y, z) into 16 bits per field (csrc/sparse_hash.cuh): coordinates outside that range --
+        or so close to it that a neighbour probe c +- 2 * 16 (5^3 kernel, tensor stride 16) would leave it -- would silently
+        alias other voxels.  One min/max reduction per manager (a size-agnostic SceneGraph validates when its inputs change
+        shape, not per replay: its coordinates are the caller's responsibility)."""
+        if coords.shape[0] == 0 or getattr(CoordinateManager, "_skip_validation", False):
+            return
+        lo, hi = torch.aminmax(coords, dim=0)
+        lo, hi = lo.tolist(), hi.tolist()
+        margin = 64
+        if lo[0] < 0 or hi[0] >= 65535 or min(lo[1:]) < -32768 + margin or max(hi[1:]) > 32767 - margin:
+            raise ValueError("voxel coordinates out of range: batch index in [0, 65534], x / y / z in [%d, %d] "
+                             "(got batch %d..%d, xyz %d..%d)" % (-32768 + margin, 32767 - margin, lo[0], hi[0], min(lo[1:]), max(hi[1:])))
 
     # ------------------------------------------------------------------ everything a U-Net needs, one enqueue + one sync
     @classmethod

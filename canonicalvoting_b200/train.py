@@ -24,8 +24,10 @@ def collate(scenes):
             cat("class_labels", torch.int64))
 
 
-def joint_loss(out_f, xyz_labels, scale_labels, class_labels, log_scale=True, xyz_factor=1.0, scale_factor=1.0):
-    """train_joint.py:253-283: per-class xyz / scale heads gathered by the GT class, masked MSE x2 + 10-way CE."""
+def joint_loss(out_f, xyz_labels, scale_labels, class_labels, log_scale=True, xyz_factor=1.0, scale_factor=1.0, xyz_weights=None):
+    """train_joint.py:253-283: per-class xyz / scale heads gathered by the GT class, masked MSE x2 + 10-way CE.  `xyz_weights`
+    ([3], config xyz_component_weights, train_joint.py:241,271-272) weighs the three components of both regression terms; the
+    cross-entropy term is added only when the batch holds an object point, like the script (:269-273)."""
     nc = NCLASSES
     idx = class_labels.clone()
     idx[(idx < 0) | (idx == nc)] = 0
@@ -34,17 +36,20 @@ def joint_loss(out_f, xyz_labels, scale_labels, class_labels, log_scale=True, xy
     scale = torch.gather(out_f[:, 3 * nc:6 * nc].reshape(-1, nc, 3), 1, idx)[:, 0]
     logits = out_f[:, 6 * nc:]
     mask = (class_labels < nc) & (class_labels >= 0)
-    loss = F.cross_entropy(logits, class_labels)
+    loss = out_f.sum() * 0.0
     if bool(mask.any()):
+        w = 1.0 if xyz_weights is None else torch.as_tensor(xyz_weights, dtype=out_f.dtype, device=out_f.device).view(1, 3)
         tgt = torch.log(scale_labels[mask]) if log_scale else scale_labels[mask]
-        loss = loss + scale_factor * torch.mean((scale[mask] - tgt) ** 2) + xyz_factor * torch.mean((xyz[mask] - xyz_labels[mask]) ** 2)
+        loss = loss + scale_factor * torch.mean((scale[mask] - tgt) ** 2 * w) + xyz_factor * torch.mean((xyz[mask] - xyz_labels[mask]) ** 2 * w)
+        loss = loss + F.cross_entropy(logits, class_labels)
     return loss
 
 
 def train_step(model, optimizer, batch, device):
     """One optimisation step on this rank's batch; `model` may be wrapped in DistributedDataParallel."""
     coords, feats, xyz_l, scale_l, class_l = batch
-    feats = feats * 2.0 - 1.0                                                  # train_joint.py:248-249
+    feats = feats.clone()
+    feats[:, -3:] = feats[:, -3:] * 2.0 - 1.0                                  # train_joint.py:248-249: only the rgb columns are recentred
     optimizer.zero_grad(set_to_none=True)
     out = model(ME.SparseTensor(feats.to(device), coords.to(device), device=device))
     loss = joint_loss(out.F, xyz_l.to(device), scale_l.to(device), class_l.to(device))

@@ -266,6 +266,20 @@ int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t stem_ksize,
 #define CVB200_OP_CONV_TC_GATHER4 3 /* tcgen05 convolution of a 4-channel input (ldi = 4; the 3-channel stem padded with a zero
                                    * channel): table [n_out, k3], w = [cout][K], K = cin = 32*ceil(k3/8), w[co][4*k + c]; the
                                    * kernel gathers 8 neighbours x 4 channels per k-block, no im2col matrix */
+/* Head decode of the joint model fused into the epilogue of the LAST convolution of a program (`final`, utils/minkunet.py:114 ->
+ * eval_joint.py:173-193): instead of storing its [n, 64] output the kernel decodes every row while it sits in registers and
+ * writes what cvb200_head_decode_points would write -- the N x 64 float32 round trip through HBM disappears.  Needs
+ * nclasses == 9 (64 channels = one tile column block); outputs as in cvb200_head_decode_points, d_coords / d_points may be NULL. */
+typedef struct cvb200_decode_args {
+    float *xyz, *scale;        /* [n,3] each */
+    int64_t *class_pred;       /* [n] */
+    float *prob;               /* [n] */
+    const int32_t *coords;     /* [n,4] rows (batch, x, y, z), or NULL */
+    float *points;             /* [n,3] = coords[:, 1:4] * res, or NULL */
+    float res;
+    int32_t nclasses, log_scale;
+} cvb200_decode_args;
+
 typedef struct cvb200_sc_op {
     int32_t kind, cin, cout, k3;
     int32_t ldi, ldo, ldr, relu;
@@ -281,10 +295,22 @@ typedef struct cvb200_sc_op {
                                * kernel plans its work itself -- the launch does not depend on a size the host would have to read
                                * back, so a whole program can be captured into one CUDA graph and replayed for any scene of that
                                * bucket.  Tensor-core kinds only. */
+    const cvb200_decode_args *decode; /* NULL, or: do not store `out` (may be NULL then), decode the rows instead (see above); HOST pointer */
 } cvb200_sc_op;
 
 /* Launch the ops of a program in order on `stream` (host array of ops; asynchronous). */
 int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, void *stream);
+
+/* CUDA-graph capture of a sequence of launches of this library (and of anything else enqueued on `stream` and on streams
+ * forked from / joined to it in between): begin, enqueue, end -> executable graph; launch it on any stream any number of times.
+ * use_node_priority: kernels keep the priority of the stream they were captured on (cudaGraphInstantiateFlagUseNodePriority) --
+ * the engine captures the coordinate-map builder on a high-priority branch.  n_nodes (may be NULL) receives the node count.
+ * cvb200_graph_abort ends a capture that went wrong.  Thread-local capture mode. */
+int cvb200_graph_begin(void *stream);
+int cvb200_graph_end(void *stream, int32_t use_node_priority, void **exec_out, int64_t *n_nodes);
+int cvb200_graph_abort(void *stream);
+int cvb200_graph_launch(void *exec, void *stream);
+int cvb200_graph_destroy(void *exec);
 
 /* Head decode of the joint model (eval_joint.py:173-190): d_feats [n, >= 7*nclasses+1] (row stride ld) =
  * xyz[C][3] | scale[C][3] | logits[C+1] -> xyz_pred [n,3], scale_pred [n,3] (exp() if log_scale,
