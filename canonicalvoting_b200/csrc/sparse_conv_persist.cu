@@ -68,7 +68,6 @@ struct PsPlan {
     int dbg;          // measurement aid (cvb200_sc_set_conv_debug): 1 no gather copies, 2 no zero-fill copies, 4 no MMA, 8 no weight TMA
     int allow_split;  // 0: never cut tiles into pieces
     int force_ks;     // probe override of ks (0 = planner's choice)
-    int lean;         // 1: producer-side proxy fence + one MMA issuer (see the gather role); 0: asynchronous arrivals + two issuers
 };
 
 struct PsHeader {
@@ -179,11 +178,11 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
 
     if (tid == 0) {
         for (int s = 0; s < P0.stages; s++) {
-            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), P0.lean ? 1 + 1 : 1 + 32);
+            tm_mbar_init(tm_smem_u32(&H.full_bar[s]), 1 + 32);
             tm_mbar_init(tm_smem_u32(&H.empty_bar[s]), 1);
         }
         for (int b = 0; b < 2; b++) {
-            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), (P0.lean || PS_DBG(P0, 0x40000)) ? 1 : 2);      // both MMA warps
+            tm_mbar_init(tm_smem_u32(&H.acc_full[b]), PS_DBG(P0, 0x40000) ? 1 : 2);      // both MMA warps
             tm_mbar_init(tm_smem_u32(&H.acc_empty[b]), 4);
             tm_mbar_init(tm_smem_u32(&H.turn[b]), 1);
         }
@@ -257,7 +256,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // order, stages are released in order, and the first k-block of a unit overwrites the accumulator before anything
         // is added to it.  Both warps commit to acc_full (count 2).
         const int me = warp == 4 ? 0 : 1;
-        const int issuers = (P.lean || PS_DBG(P, 0x40000)) ? 1 : 2;   // lean protocol: one issuer (warp 12 idles)
+        const int issuers = PS_DBG(P, 0x40000) ? 1 : 2;            // measurement aid: one issuer only (warp 12 idles)
         int li = 0, n_base = 0;
         for (int u = blockIdx.x; u < P.n_units && me < issuers; u += gridDim.x, li++) {
             const PsUnit U = ps_unit(P, u);
@@ -277,9 +276,10 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                 if (tr && me == 0 && lane == 0 && tn < 256) { trace[3 * tn] = t0; trace[3 * tn + 1] = clock64(); }
                 const uint32_t a_s = tm_smem_u32(stage0 + (size_t)s * stage_bytes), b_s = a_s + a_bytes;
                 const uint64_t a_desc = tm_desc_k_sw128(a_s), b_desc = tm_desc_k_sw128(b_s);
-                // cp.async wrote through the generic proxy, the tensor core reads through the async proxy: fence here, unless the
-                // producers already did before arriving (lean protocol)
-                if (!P.lean && !PS_DBG(P, 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // cp.async wrote through the generic proxy, the tensor core reads through the async proxy.  (Fencing on the producer side
+                // instead -- wait for the copy group, fence, one arrival per warp -- was measured in round 2, with one and with two
+                // issuers: 1.31-1.39 ms per scene against 1.23 ms; the asynchronous arrivals below never stall a producer.)
+                if (!PS_DBG(P, 16) && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 // my turn: the other warp has issued k-block n - 1
                 if (n > 0 && issuers == 2) tm_mbar_wait(tm_smem_u32(&H.turn[me]), (uint32_t)(((n >> 1) + me + 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -314,11 +314,7 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
         // warp placement: a scheduler (warp % 4) that hosts an MMA issuer or the TMA warp hosts no gather warp, whose long
         // instruction streams would delay the issuers' latency-critical hand-shakes
         const int w = warp < 4 ? warp - 1 : warp - 2, c = lane & 7, rb = lane >> 3;   // warps 1,2,3,5,6,7 -> 0..5
-        // producing warps: own k-blocks must be less than a ring apart (lean: strictly less than the ring minus the one k-block a
-        // warp's arrival lags behind, or the arrival would wait for its own consumption)
-        const int Wmax = P.lean ? P.stages - 1 : P.stages;
-        const int W = Wmax < kPsProducers ? Wmax : kPsProducers;
-        uint32_t pend_bar = 0;                                             // lean: full barrier of my k-block whose copies are in flight
+        const int W = P.stages < kPsProducers ? P.stages : kPsProducers;   // producing warps: own k-blocks must be less than a ring apart
         const uint32_t off_even = (uint32_t)(rb * 128 + ((c ^ rb) << 4)), off_odd = (uint32_t)((rb + 4) * 128 + ((c ^ (rb + 4)) << 4));
         const size_t ld4 = (size_t)ldi;
         int n_base = 0;
@@ -389,39 +385,12 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(id >= 0 ? 16u : 0u) : "memory");
                 }
                 }
-                if (P.lean) {
-                    // Lean protocol: the copies of this k-block form a group; the warp completes its PREVIOUS k-block -- waits for
-                    // that group, makes the data visible to the async proxy (fence.proxy.async, here instead of on the MMA
-                    // issuer's critical path) and arrives once -- so two of its k-blocks are always in flight.
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    if (pend_bar) {
-                        asm volatile("cp.async.wait_group 1;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pend_bar) : "memory");
-                        }
-                    }
-                    pend_bar = tm_smem_u32(&H.full_bar[s]);
-                } else {
-                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
-                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tm_smem_u32(&H.full_bar[s])) : "memory");
                 if (tr && tid == 32 && tn < 256) { trace[768 + 3 * tn + 2] = clock64(); }
                 tn++;
             }
             (void)k_nxt;
             n_base += U.kb1 - U.kb0;
-            // lean: the unit's last k-block of this warp must not wait for the next unit (its first k-block may belong to a tile this
-            // CTA only reaches after the epilogue freed an accumulator)
-            if (pend_bar) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pend_bar) : "memory");
-                }
-                pend_bar = 0;
-            }
         }
     } else {
         // ===== epilogue warps 8..11: TMEM lane quarter (warp & 3) -> registers -> (+bias, +residual, relu) -> global
@@ -650,7 +619,6 @@ sc_conv_persist_kernel(const __grid_constant__ CUtensorMap map_b, const float *_
 }
 
 // ---------------------------------------------------------------------------------------------------------- host side
-int g_ps_lean = 0;
 int g_ps_allow_split = 1;   // 0: never cut tiles into pieces (bit-reproducible summation order; used by the tests)
 int g_ps_use_pdl = 1;
 int g_ps_debug = 0;
@@ -696,7 +664,6 @@ static void ps_plan(int64_t n_out, int cin, int cout, int k3, PsPlan *P, int *ct
     // layers) and are no longer offered; the register budget is now spent on one CTA
     *ctas_per_sm = 1;
     P->allow_split = g_ps_allow_split;
-    P->lean = g_ps_lean;
     P->force_ks = (g_ps_debug >> 8) & 255;
     ps_plan_rows(n_out, kNumSMs * *ctas_per_sm, P);
     int stages = (kPsSmemBytes - 1024 - 16384) / stage_bytes;
@@ -778,8 +745,7 @@ extern "C" int cvb200_sc_conv_forward_tc(const float *d_in, int64_t n_in, int32_
 
 extern "C" int cvb200_sc_set_conv_options(int32_t allow_split, int32_t use_pdl) {
     cvb200::g_ps_allow_split = allow_split != 0;
-    cvb200::g_ps_use_pdl = (use_pdl & 1) != 0;
-    cvb200::g_ps_lean = (use_pdl & 2) != 0;            // measurement: bit 1 selects the lean producer / issuer protocol
+    cvb200::g_ps_use_pdl = use_pdl != 0;
     return 0;
 }
 
