@@ -508,8 +508,7 @@ def main():
     except Exception as e:  # pragma: no cover
         t_module = repr(e)
 
-    for ln in lanes + lanes_e2e:
-        del ln
+    launches_per_scene = lanes[0].launches if lanes else 0     # kernels of one scene graph: map builder, input pad, convolutions (decode fused), vote
     lanes, lanes_e2e = [], []
     torch.cuda.empty_cache()
 
@@ -557,7 +556,6 @@ def main():
                                                        "what": "unmodified hv_cuda.forward built for sm_100a (oracle/_ref)"}
         except Exception as e:  # pragma: no cover
             cpu["reference_vote_cuda_same_gpu"] = {"error": repr(e)}
-        launches_per_scene = len(arr) + 1 + 29 + 1 + 2      # convolutions, input pad, map builder, decode, vote (scatter, write-out)
         ms_step = 1e3 * t_resident / args.steps
         line = {
             "metric": "scenes_per_sec", "value": world * args.steps / t_resident, "unit": "scenes/s",

@@ -93,7 +93,7 @@ class MapsLayout(ctypes.Structure):
     _fields_ = [("total_bytes", _i64), ("capacity", _i64), ("counts", _i64), ("arange", _i64), ("stem_table", _i64),
                 ("coords", _i64 * 5), ("keys", _i64 * 5), ("vals", _i64 * 5), ("nbr3", _i64 * 5),
                 ("children", _i64 * 4), ("up_table", _i64 * 4), ("parent", _i64 * 4), ("koff", _i64 * 4),
-                ("flag", _i64), ("scan", _i64), ("cub_temp", _i64), ("cub_temp_bytes", _i64)]
+                ("flag", _i64), ("scan", _i64), ("cub_temp", _i64), ("cub_temp_bytes", _i64), ("fill_ff", _i64), ("fill_ff_bytes", _i64)]
 
 
 SIGNATURES.update({

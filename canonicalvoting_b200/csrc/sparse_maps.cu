@@ -1,5 +1,8 @@
 // canonicalvoting_b200/csrc/sparse_maps.cu -- all coordinate levels and kernel maps of the U-Net in ONE enqueue.
 //
+// Round 2: 33 graph nodes per scene instead of 56 -- everything that starts as all-ones lies in one region (one memset instead of
+// fifteen), the row counts and the identity table are written by the kernels that know them (no one-thread kernels).
+//
 // sparse_coords.cu exposes the coordinate manager step by step (the module path mirrors MinkowskiEngine's lazy
 // behaviour: a level or kernel map is created when the first layer asks for it) and reads the size of every new
 // level back to the host: 4 blocking reads + ~45 launches issued from Python per scene, 1.2 ms of host time for a
@@ -25,18 +28,14 @@ namespace cvb200 {
 constexpr int kMapThreads = 256;
 constexpr int kMapBlocks = 4 * kNumSMs;
 
-__global__ void mp_set_count_kernel(int *counts, int level, int value) { counts[level] = value; }
-
-__global__ void mp_arange_kernel(int *out, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
-}
-
-__global__ void mp_insert_rows_kernel(const int4 *__restrict__ coords, const int *__restrict__ cnt, unsigned long long *keys, int *vals,
-                                      unsigned int mask) {
-    const int n = *cnt;
+// level 0: hash the input rows; the same pass writes the identity table of the 1x1x1 convolutions and the level's row count
+__global__ void mp_insert_rows_kernel(const int4 *__restrict__ coords, int n, unsigned long long *keys, int *vals, unsigned int mask,
+                                      int *__restrict__ arange, int *__restrict__ counts) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 c = __ldg(coords + i);
         vals[hash_insert(keys, mask, pack_coord(c.x, c.y, c.z, c.w))] = i;
+        arange[i] = i;
     }
 }
 
@@ -49,7 +48,8 @@ __global__ void mp_insert_coarse_min_kernel(const int4 *__restrict__ coords, con
     const int n = *cnt;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 c = mp_coarse_of(__ldg(coords + i), shift);
-        atomicMin(vals + hash_insert(keys, mask, pack_coord(c.x, c.y, c.z, c.w)), i);   // vals pre-filled with INT_MAX
+        // vals pre-filled with 0xffffffff (the same memset as the keys and the tables): unsigned minimum
+        atomicMin(reinterpret_cast<unsigned int *>(vals) + hash_insert(keys, mask, pack_coord(c.x, c.y, c.z, c.w)), (unsigned int)i);
     }
 }
 
@@ -68,14 +68,12 @@ __global__ void mp_first_child_kernel(const int4 *__restrict__ coords, const int
     }
 }
 
-__global__ void mp_count_coarse_kernel(const int *__restrict__ flag, const int *__restrict__ excl, int n_ub, int *counts, int level) {
-    counts[level] = excl[n_ub - 1] + flag[n_ub - 1];
-}
-
+// numbers the coarse voxels (rank of the first child) and records how many there are: counts[level + 1]
 __global__ void mp_number_coarse_kernel(const int4 *__restrict__ coords, const int *__restrict__ cnt, int shift,
                                         const int *__restrict__ flag, const int *__restrict__ excl, unsigned long long *keys, int *vals,
-                                        unsigned int mask, int4 *__restrict__ out_coords) {
+                                        unsigned int mask, int4 *__restrict__ out_coords, int n_ub, int *__restrict__ count_out) {
     const int n = *cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = excl[n_ub - 1] + flag[n_ub - 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (!flag[i]) continue;
         const int4 c = mp_coarse_of(__ldg(coords + i), shift);
@@ -147,15 +145,17 @@ extern "C" int cvb200_sc_maps_layout(int64_t n, int32_t stem_ksize, int32_t n_do
     auto take = [&](int64_t bytes) { const int64_t o = off; off += align256(bytes); return o; };
     L->counts = take(64);
     L->arange = take(4 * n);
+    // everything that starts as all-ones (-1 table entries, empty hash keys, "no first child yet") is contiguous: ONE memset
+    L->fill_ff = off;
     L->stem_table = stem_ksize ? take(4 * n * stem_ksize * stem_ksize * stem_ksize) : 0;
-    for (int l = 0; l <= n_down; l++) {
-        L->coords[l] = l ? take(16 * n) : 0;
-        L->keys[l] = take(8 * cap);
-        L->vals[l] = take(4 * cap);
-        L->nbr3[l] = take(4 * n * 27);
-    }
+    for (int l = 0; l <= n_down; l++) L->nbr3[l] = take(4 * n * 27);
+    for (int l = 0; l <= n_down; l++) L->keys[l] = take(8 * cap);
+    for (int l = 1; l <= n_down; l++) L->vals[l] = take(4 * cap);
+    for (int l = 0; l < n_down; l++) L->children[l] = take(32 * n);
+    L->fill_ff_bytes = off - L->fill_ff;
+    L->vals[0] = take(4 * cap);
+    for (int l = 1; l <= n_down; l++) L->coords[l] = take(16 * n);
     for (int l = 0; l < n_down; l++) {
-        L->children[l] = take(32 * n);
         L->up_table[l] = take(32 * n);
         L->parent[l] = take(4 * n);
         L->koff[l] = take(4 * n);
@@ -183,12 +183,8 @@ extern "C" int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t 
     auto vals = [&](int l) { return (int *)(ws + L->vals[l]); };
     auto coords = [&](int l) { return l ? (const int4 *)(ws + L->coords[l]) : (const int4 *)d_coords; };
 
-    mp_set_count_kernel<<<1, 1, 0, stream>>>(counts, 0, n_ub);
-    mp_arange_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>((int *)(ws + L->arange), n_ub);
-    CVB_CUDA(cudaMemsetAsync(keys(0), 0xff, 8 * (size_t)L->capacity, stream));
-    mp_insert_rows_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(0), counts, keys(0), vals(0), mask);
-    if (stem_ksize) CVB_CUDA(cudaMemsetAsync(ws + L->stem_table, 0xff, 4 * (size_t)n_ub * stem_ksize * stem_ksize * stem_ksize, stream));
-    for (int l = 0; l <= n_down; l++) CVB_CUDA(cudaMemsetAsync(ws + L->nbr3[l], 0xff, 4 * (size_t)n_ub * 27, stream));
+    CVB_CUDA(cudaMemsetAsync(ws + L->fill_ff, 0xff, (size_t)L->fill_ff_bytes, stream));
+    mp_insert_rows_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(0), n_ub, keys(0), vals(0), mask, (int *)(ws + L->arange), counts);
     if (stem_ksize)
         mp_kernel_map_kernel<<<8 * kMapBlocks, kMapThreads, 0, stream>>>(coords(0), counts, keys(0), vals(0), mask, stem_ksize, 1,
                                                                         (int *)(ws + L->stem_table));
@@ -196,16 +192,12 @@ extern "C" int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t 
     for (int l = 0; l < n_down; l++) {
         const int shift = l + 1;
         int *flag = (int *)(ws + L->flag), *scan = (int *)(ws + L->scan);
-        CVB_CUDA(cudaMemsetAsync(keys(l + 1), 0xff, 8 * (size_t)L->capacity, stream));
-        CVB_CUDA(cudaMemsetAsync(vals(l + 1), 0x7f, 4 * (size_t)L->capacity, stream));
-        CVB_CUDA(cudaMemsetAsync(ws + L->children[l], 0xff, 32 * (size_t)n_ub, stream));
         mp_insert_coarse_min_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(l), counts + l, shift, keys(l + 1), vals(l + 1), mask);
         mp_first_child_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(l), counts + l, n_ub, shift, keys(l + 1), vals(l + 1), mask, flag);
         size_t temp = (size_t)L->cub_temp_bytes;
         CVB_CUDA(cub::DeviceScan::ExclusiveSum(ws + L->cub_temp, temp, (const int *)flag, scan, n_ub, stream));
-        mp_count_coarse_kernel<<<1, 1, 0, stream>>>(flag, scan, n_ub, counts, l + 1);
         mp_number_coarse_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(l), counts + l, shift, flag, scan, keys(l + 1), vals(l + 1), mask,
-                                                                       (int4 *)(ws + L->coords[l + 1]));
+                                                                       (int4 *)(ws + L->coords[l + 1]), n_ub, counts + l + 1);
         mp_link_children_kernel<<<kMapBlocks, kMapThreads, 0, stream>>>(coords(l), counts + l, shift, keys(l + 1), vals(l + 1), mask,
                                                                        (int *)(ws + L->parent[l]), (int *)(ws + L->koff[l]),
                                                                        (int *)(ws + L->children[l]), (int *)(ws + L->up_table[l]));

@@ -62,6 +62,29 @@ def _fold(conv, bn):
     return w, b
 
 
+def pack_conv(conv, bn, gather4=True):
+    """(weight, bias, op kind, gather width) of one convolution (+ folded eval-mode BatchNorm) as cvb200_sc_run_program takes it:
+    output channels padded to a multiple of 16; cin % 32 == 0: kind 0, weight [k3, cout, cin]; a <= 4-channel input (the 5^3
+    stem): kind 3, the input padded to 4 channels, 8 neighbours x 4 channels per k-block, weight [1, cout, 32 ceil(k3 / 8)];
+    anything else: None (the caller falls back)."""
+    w, b = _fold(conv, bn)
+    cin = w.shape[1]
+    if w.shape[2] % 16:      # the tensor-core kernel needs cout % 16 == 0 (the 8-channel heads of the per-category models,
+        pad = 16 - w.shape[2] % 16          # eval_separate.py:138): zero output channels, cut off again by the caller
+        w = torch.nn.functional.pad(w, (0, pad))
+        b = torch.nn.functional.pad(b, (0, pad)) if b is not None else None
+    b = b.contiguous() if b is not None else None
+    if cin % 32 == 0:
+        return w.transpose(1, 2).contiguous(), b, 0, 0
+    if cin <= 4 and gather4:
+        k3, cout = w.shape[0], w.shape[2]
+        kp = 32 * ((k3 + 7) // 8)
+        w4 = torch.zeros((kp // 4, 4, cout), dtype=w.dtype, device=w.device)
+        w4[:k3, :cin] = w
+        return w4.reshape(1, kp, cout).transpose(1, 2).contiguous(), b, 3, k3
+    return None
+
+
 class _Slice:
     """Column slice [c0, c0+c) of a row-major float32 matrix [rows, ld] that lives at byte address `base`."""
     __slots__ = ("base", "rows", "ld", "c0", "c")
@@ -535,7 +558,7 @@ class SceneGraph:
                     torch.cuda.synchronize(dev)
                 finally:
                     L.cvb200_sc_set_conv_options(*CONV_OPTIONS)
-        self.launches = len(arr) + 29 + (0 if fuse_decode else 1) + (1 if pad4 else 0) + (2 if vote else 0)
+        self.launches = len(arr) + 31 + (0 if fuse_decode else 1) + (1 if pad4 else 0) + (2 if vote else 0)
 
     def run(self, coords, feats):
         """Copy one scene's inputs (int32 [n,4] coordinates, float32 [n,C] features; pinned host or device tensors) into the

@@ -195,6 +195,15 @@ class CoordinateManager:
         cm.enqueue = enqueue
         return cm
 
+    def identity_table(self, tensor_stride):
+        """[n, 1] table row -> row: a 1x1x1 convolution as the one primitive."""
+        key = ("ident", tensor_stride)
+        t = self._nbr.get(key)
+        if t is None:
+            t = torch.arange(self.levels[tensor_stride].n, dtype=torch.int32, device=self.device).view(-1, 1).contiguous()
+            self._nbr[key] = t
+        return t
+
     # ------------------------------------------------------------------ stride-1 kernel maps
     def kernel_map(self, tensor_stride, ksize):
         self._maybe_fill_unet(tensor_stride, ksize)

@@ -249,6 +249,7 @@ typedef struct cvb200_sc_maps_layout_t {
     int64_t coords[5], keys[5], vals[5], nbr3[5];
     int64_t children[4], up_table[4], parent[4], koff[4];
     int64_t flag, scan, cub_temp, cub_temp_bytes;
+    int64_t fill_ff, fill_ff_bytes;      /* the region cvb200_sc_build_maps starts by filling with 0xff (tables, keys, first-child slots) */
 } cvb200_sc_maps_layout_t;
 int cvb200_sc_maps_layout(int64_t n, int32_t stem_ksize, int32_t n_down, cvb200_sc_maps_layout_t *layout);
 int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t stem_ksize, int32_t n_down, void *d_workspace,

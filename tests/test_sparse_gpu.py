@@ -557,3 +557,38 @@ def test_out_of_range_coordinates_are_rejected():
         c = torch.cat([ok[:2], torch.tensor(bad, dtype=torch.int32)])
         with pytest.raises(ValueError, match="out of range"):
             ME.SparseTensor(feats, c, device="cuda")
+
+
+def test_module_path_defers_and_fuses_in_inference():
+    """The unchanged reference call sequence (conv -> norm -> relu, residual blocks, ME.cat, 1x1x1 down-samples, transposed
+    convolutions) under torch.no_grad(): convolutions are deferred and launched as the engine's fused op (BatchNorm folded,
+    bias + residual + ReLU in the epilogue).  Same numbers as MinkUNetEngine on the same model; with autograd on nothing is deferred."""
+    from canonicalvoting_b200 import sparse as ME
+    from canonicalvoting_b200.engine import MinkUNetEngine
+    from canonicalvoting_b200.minkunet import MinkUNet34C
+    from canonicalvoting_b200.sparse import functional as Fn
+    torch.manual_seed(4)
+    coords, feats = _scene(n=5000, G=40, batch=2, cin=3, seed=21)
+    model = MinkUNet34C(3, 64).cuda().eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.8, 1.2); m.weight.uniform_(0.8, 1.2); m.bias.normal_(0, 0.05)
+    eng = MinkUNetEngine(model)
+    want = eng(coords.cuda(), feats.cuda())
+    Fn.set_forward_mode("auto")
+    with torch.no_grad():
+        st = model(ME.SparseTensor(feats, coords, device="cuda"))
+        assert st._pending is not None                     # `final` itself is still deferred until somebody reads .F
+        got = st.F
+    scale = float(want.abs().max())
+    assert got.shape == want.shape and float((got - want).abs().max()) <= 1e-3 * scale     # same kernels; split tiles sum in arrival order
+    Fn.set_forward_mode("fp32")
+    with torch.no_grad():
+        exact = model(ME.SparseTensor(feats, coords, device="cuda")).F
+    assert float((got - exact).abs().max()) <= 6e-3 * scale                                 # TF32 vs exact fp32
+    # training mode / autograd: the step-by-step path, BatchNorm with batch statistics
+    Fn.set_forward_mode("auto")
+    model.train()
+    out = model(ME.SparseTensor(feats, coords, device="cuda"))
+    assert out._pending is None and out.F.requires_grad
