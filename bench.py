@@ -245,7 +245,7 @@ def train_c3(args, dev, rank, world, local):
         ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
         opt = torch.optim.Adam(model.parameters(), lr=1e-3)
         mine = train.shard_scenes(scenes_per_gpu * world, rank, world)
-        batch = train.collate([synthetic.make_scene(50000, 128, 12, seed=1000 + i) for i in mine])
+        batch = tuple(t.pin_memory() for t in train.collate([synthetic.make_scene(50000, 128, 12, seed=1000 + i) for i in mine]))
         for _ in range(warm):
             loss = train.train_step(ddp, opt, batch, dev)
         torch.cuda.synchronize()

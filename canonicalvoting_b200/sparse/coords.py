@@ -59,10 +59,10 @@ class CoordinateManager:
         self.levels = {1: Level(coords.contiguous(), 1)}
         self._nbr = {}      # (tensor_stride, ksize) -> [n, ksize^3] int32
         self._down = {}     # fine tensor_stride -> dict(children, up_table, parent, koff)
-        # Inference (autograd off): the first map a layer asks for triggers ONE fused build of everything a U-Net needs (four
-        # stride-2 levels, their 3^3 maps, children / parent tables) with one host synchronisation, instead of a read-back per
-        # level; whatever a network asks beyond that is still built step by step on the same hash tables.
-        self._lazy_unet = not torch.is_grad_enabled()
+        # The first map a layer asks for triggers ONE fused build of everything a U-Net needs (four stride-2 levels, their 3^3
+        # maps, children / parent tables) with one host synchronisation, instead of a read-back per level; whatever a network
+        # asks beyond that is still built step by step on the same hash tables (identical numbering, tests/test_sparse_gpu.py).
+        self._lazy_unet = True
 
     @staticmethod
     def _validate(coords):

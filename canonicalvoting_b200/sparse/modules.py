@@ -225,6 +225,10 @@ class MinkowskiConvolution(_ConvBase):
         if self.kernel_size == 1 and self.stride == 1:
             if defer:
                 return x._deferred(_Pending(self, x.F, cm.identity_table(ts)))
+            if resolve_mode() == "tf32" and self.in_channels % 32 == 0 and self.out_channels % 32 == 0:
+                # training in tf32 mode: the same tensor-core kernels (forward, input and weight gradient) on an identity table
+                ident = cm.identity_table(ts)
+                return x._like(sparse_conv(x.F, self.kernel.unsqueeze(0), self.bias, ident, ident, "same"))
             f = x.F @ self.kernel                      # plain library GEMM (1x1x1 convolution)
             if self.bias is not None:
                 f = f + self.bias

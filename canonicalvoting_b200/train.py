@@ -48,11 +48,12 @@ def joint_loss(out_f, xyz_labels, scale_labels, class_labels, log_scale=True, xy
 def train_step(model, optimizer, batch, device):
     """One optimisation step on this rank's batch; `model` may be wrapped in DistributedDataParallel."""
     coords, feats, xyz_l, scale_l, class_l = batch
-    feats = feats.clone()
-    feats[:, -3:] = feats[:, -3:] * 2.0 - 1.0                                  # train_joint.py:248-249: only the rgb columns are recentred
     optimizer.zero_grad(set_to_none=True)
-    out = model(ME.SparseTensor(feats.to(device), coords.to(device), device=device))
-    loss = joint_loss(out.F, xyz_l.to(device), scale_l.to(device), class_l.to(device))
+    nb = dict(non_blocking=True)          # pinned batches (a DataLoader with pin_memory) upload asynchronously
+    feats = feats.to(device, **nb).clone()
+    feats[:, -3:] = feats[:, -3:] * 2.0 - 1.0                                  # train_joint.py:248-249: only the rgb columns are recentred
+    out = model(ME.SparseTensor(feats, coords.to(device, **nb), device=device))
+    loss = joint_loss(out.F, xyz_l.to(device, **nb), scale_l.to(device, **nb), class_l.to(device, **nb))
     loss.backward()
     optimizer.step()
     return loss.detach()
