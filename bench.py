@@ -36,9 +36,9 @@ import numpy as np  # noqa: E402
 
 NCLASSES = 9
 # DRAM bytes per call of the vote op (sum over its kernels) from this round's ncu --set full capture; None where no capture exists
-VOTE_DRAM_BYTES_NCU = {}
-# same for the convolution program (sum over its launches); filled in from this round's capture
-CONV_DRAM_BYTES_NCU = {}
+VOTE_DRAM_BYTES_NCU = {"C2": 21725184 + 80819456}      # scatter + write-out, profiles/r2g_launches_scene_C2.csv (third scene)
+# same for the convolution program: sum over its 63 launches of the third scene of that launch list (cold caches between launches)
+CONV_DRAM_BYTES_NCU = {"C2": 569001472}
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -575,8 +575,8 @@ def main():
             "gpu_launches": launches_per_scene * args.steps,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
                          "traffic": CONV_DRAM_BYTES_NCU.get(args.workload),
-                         "traffic_source": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the convolution launches of one scene, "
-                                           "ncu capture of this round (profiles/)",
+                         "traffic_source": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the 63 convolution launches of one scene, "
+                                           "ncu launch list of round 2 (profiles/r2g_launches_scene_C2.csv, r2g_per_layer_C2.txt)",
                          "peak_source": peak_src + ": bf16 sustained / 2 (kind::tf32 runs at half the bf16 rate)",
                          "kernel": "sc_conv_persist_kernel program of the U-Net (%d fused convolutions), one scene alone, L2 flushed" % len(arr),
                          "algorithmic_flops": flops, "executed_flops": executed, "kernel_ms": unet_med,
@@ -586,8 +586,8 @@ def main():
                          "vote": {"bound": "hbm", "achieved": vote_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": vote_gbs / hbm_gbs,
                                   "kernel": "hv_scatter_kernel + hv_finalize_kernel", "algorithmic_bytes": vbytes,
                                   "kernel_ms": vote_med, "traffic": VOTE_DRAM_BYTES_NCU.get(args.workload),
-                                  "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two kernels, ncu --set full capture of "
-                                                    "this round (profiles/)"}},
+                                  "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two kernels (profiles/r2g_launches_scene_C2.csv, "
+                                                    "r2g_ncu_full_vote.csv)"}},
             "cpu_baseline": cpu,
             "train_C3": train,
             "clocks": clk.summary(),
