@@ -145,7 +145,6 @@ def workload_config(workload, sc):
                         "scene, N=%d voxels, vote grid %d^3, num_rots=%d" % (workload, len(sc["points"]), G, sc["num_rots"]),
             "points": len(sc["points"]), "grid": [G, G, G], "num_rots": sc["num_rots"], "res": sc["res"],
             "weights": "random init (no checkpoint offline), BatchNorm in eval mode",
-            "scenes_in_flight_per_gpu": None,
             "l2": "value/e2e: inputs larger than L2 (rotation of 4 resident scenes, ~200 MB working set each); "
                   "roofline kernel_ms: L2 flushed (256 MiB memset) right before the convolution program of every timed step"}
 
@@ -311,15 +310,11 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    try:       # one host thread per rank drives everything: keep the ranks of a node on separate cores
-        ncpu = os.cpu_count() or 1
-        per = max(1, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
-        os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
-    except Exception:
-        pass
     if world > 1:
+        import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies takes the job down within minutes instead of leaving the others in a collective until somebody kills them
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     # weak scaling: every rank owns its own scenes (scene i -> rank i mod W); no data-path collective
     sc = scene_for(args.workload, seed=rank)
@@ -537,10 +532,11 @@ def main():
         tf32_peak = bf16_tf / 2.0
         vbytes = vote_bytes(n, dims)
         vote_gbs = vbytes / (vote_med * 1e-3) / 1e9
-        cpu = cpu_baseline(model_cpu, args.workload, sc, args.cpu_seconds)
+        # the CPU ports on the host cores: at N = 1 only (the other ranks of a multi-GPU run would idle through it)
+        cpu = cpu_baseline(model_cpu, args.workload, sc, args.cpu_seconds) if world == 1 else {"skipped": "reported at N = 1 only"}
         try:   # the reference's own CUDA vote kernel (unmodified, built for sm_100a) on this same GPU, reported beside it
             from oracle import build_ref
-            ref = build_ref.load_ref()
+            ref = build_ref.load_ref() if world == 1 else None
             if ref is not None:
                 xyz, scale, cls, prob = engine.predict(coords_d, feats_d)
                 for _ in range(3):
@@ -564,7 +560,7 @@ def main():
             "step_ms_flushed": {"median": float(np.median(step_ms)), "min": float(np.min(step_ms)), "max": float(np.max(step_ms))},
             "host_us_per_scene": host_us_per_scene,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (U-Net) / f32 (vote)",
-            "data": "synthetic", "config": dict(workload_config(args.workload, sc), scenes_in_flight_per_gpu=L),
+            "data": "synthetic", "config": workload_config(args.workload, sc), "scenes_in_flight_per_gpu": L,
             "e2e": {"value": world * args.steps / t_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "result": "boxes [K,8,3] + scores + classes of the candidate loop (eval_joint.py:255-263) + vote-map peak; K = %.2f boxes per "
                               "scene with these randomly initialised weights" % (n_boxes / max(args.steps, 1)),
