@@ -234,10 +234,10 @@ def test_training_step_tf32_gradients_match_oracle_autograd(bn_training):
     # envelopes = what was measured on B200 (printed above) with a margin of 2-3x:
     #   bn-eval   fp32 1.1e-6 global / 2.2e-4 worst tensor;   tf32 1.4e-3 global, cosine 0.999999, 8.7e-2 worst tensor (a BatchNorm bias:
     #             a sum over all rows with cancellation), 2.1e-2 median
-    #   bn-train  fp32 2.6e-3 global, cosine 0.999997;         tf32 7.1e-2 global, cosine 0.9975, 1.5e-1 worst tensor
+    #   bn-train  fp32 2.6e-3 global, cosine 0.999997;         tf32 7.1e-2 global, cosine 0.9975, 1.5e-1 worst tensor (ill-conditioned: wide margin)
     if not bn_training:
         assert f["global_rel"] <= 1e-5 and f["worst"] <= 1e-3, f
-        assert t["global_rel"] <= 4e-3 and t["worst"] <= 0.2 and t["median"] <= 5e-2 and t["cosine"] >= 0.99999, t
+        assert t["global_rel"] <= 5e-3 and t["worst"] <= 0.3 and t["median"] <= 6e-2 and t["cosine"] >= 0.99999, t
     else:
         assert f["global_rel"] <= 8e-3 and f["cosine"] >= 0.9999, f
-        assert t["cosine"] >= 0.995 and t["global_rel"] <= 0.12 and t["worst"] <= 0.3, t
+        assert t["cosine"] >= 0.99 and t["global_rel"] <= 0.2 and t["worst"] <= 0.5, t
