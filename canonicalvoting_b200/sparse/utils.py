@@ -96,3 +96,38 @@ def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
     std = torch.nn.init.calculate_gain(nonlinearity, a) / math.sqrt(fan)
     with torch.no_grad():
         return tensor.normal_(0, std)
+
+
+def permute_kernel_offsets(state_dict, order="zyx"):
+    """The one-line hook for checkpoints whose kernel-offset order differs from the one this package restates from recollection
+    of MinkowskiEngine 0.5.x (offset index k = ix + K (iy + K iz): x fastest).
+    Returns a copy of `state_dict` with axis 0 of every K^3-offset convolution kernel ([K^3, Cin, Cout], K^3 in {8, 27, 125})
+    re-ordered from `order` to the package's order:
+
+        order="zyx"     the checkpoint numbers offsets with z fastest (k' = iz + K (iy + K ix))
+        order="mirror"  the checkpoint's offsets are point-mirrored (k' = K^3 - 1 - k)
+        order=callable  perm = order(K) -> LongTensor [K^3] with new_kernel[k] = old_kernel[perm[k]]
+
+        model.load_state_dict(permute_kernel_offsets(torch.load("pretrained/joint.pth")))      # eval_joint.py:152
+
+    Applying "zyx" (or "mirror") twice gives the original back.  1x1x1 kernels ([Cin, Cout]) and all other entries pass through."""
+    import torch
+    out = {}
+    for name, t in state_dict.items():
+        k3 = t.shape[0] if (name.endswith(".kernel") and t.dim() == 3) else 0
+        K = round(k3 ** (1.0 / 3)) if k3 else 0
+        if K and K ** 3 == k3 and K > 1:
+            if callable(order):
+                perm = order(K)
+            elif order == "zyx":
+                k = torch.arange(k3)
+                ix, iy, iz = k % K, (k // K) % K, k // (K * K)
+                perm = iz + K * (iy + K * ix)          # our offset (ix, iy, iz) lives at index iz + K (iy + K ix) of the checkpoint
+            elif order == "mirror":
+                perm = torch.arange(k3 - 1, -1, -1)
+            else:
+                raise ValueError("order must be 'zyx', 'mirror' or a callable K -> permutation")
+            out[name] = t[perm.to(t.device)].clone()
+        else:
+            out[name] = t
+    return out

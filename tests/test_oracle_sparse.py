@@ -202,3 +202,28 @@ def test_grad_net_is_the_fast_net_with_autograd_leaves():
                 p[idx] -= sgn * eps
         fd = (vals[0] - vals[1]) / (2 * eps)
         assert abs(fd - float(grads[name][idx])) <= 2e-2 * max(abs(fd), 1e-3), (name, fd, float(grads[name][idx]))
+
+
+def test_kernel_offset_permutation_hook():
+    """sparse.utils.permute_kernel_offsets: a checkpoint whose kernels number the offsets with z fastest computes, after the hook,
+    the same convolution with this package's x-fastest maps (checked by swapping the x and z axes of the scene under the oracle);
+    the hook is an involution and leaves 1x1x1 kernels and every other entry alone."""
+    from canonicalvoting_b200.sparse.utils import permute_kernel_offsets
+    g = torch.Generator().manual_seed(9)
+    lin = torch.randperm(12 ** 3, generator=g)[:300]
+    coords = torch.stack([torch.zeros_like(lin), lin // 144, (lin // 12) % 12, lin % 12], 1).int()
+    feats = torch.randn(300, 4, generator=g).double()
+    for K in (3, 5):
+        w_ckpt = torch.randn(K ** 3, 4, 6, generator=g).double()
+        state = {"conv.kernel": w_ckpt, "down.kernel": torch.randn(4, 6).double(), "bn.bn.weight": torch.ones(6)}
+        fixed = permute_kernel_offsets(state, "zyx")
+        swapped = coords[:, [0, 3, 2, 1]].contiguous()                 # z-fastest numbering on (x, y, z) == x-fastest numbering on (z, y, x)
+        want = SO.conv_same(swapped, feats, w_ckpt, K)
+        got = SO.conv_same(coords, feats, fixed["conv.kernel"], K)
+        assert float((got - want).abs().max()) <= 1e-12
+        assert fixed["down.kernel"] is state["down.kernel"] and fixed["bn.bn.weight"] is state["bn.bn.weight"]
+        assert torch.equal(permute_kernel_offsets(fixed, "zyx")["conv.kernel"], w_ckpt)
+        mir = permute_kernel_offsets(state, "mirror")["conv.kernel"]
+        assert torch.equal(mir, w_ckpt.flip(0)) and torch.equal(permute_kernel_offsets({"conv.kernel": mir}, "mirror")["conv.kernel"], w_ckpt)
+        ident = permute_kernel_offsets(state, lambda k: torch.arange(k ** 3))["conv.kernel"]
+        assert torch.equal(ident, w_ckpt)
