@@ -15,49 +15,6 @@ int launch_conv_persist(const float *d_in, int64_t n_in, int ldi, int cin, const
                         int64_t n_out, int k3, const float *d_bias, const float *d_res, int ldr, int relu, float *d_out, int ldo,
                         cudaStream_t stream, int g4, const int32_t *d_n_out, const cvb200_decode_args *decode = nullptr);
 
-// Convolution with a tiny input width (the 3-channel 5^3 stem, utils/minkunet.py:53): one warp per output row, the
-// whole kernel (K^3 x cin x cout) in shared memory, lanes = output channels; neighbour ids are read 32 at a time and
-// only existing neighbours are visited.
-constexpr int kStemThreads = 256;
-
-__global__ void __launch_bounds__(kStemThreads)
-sc_conv_smallcin_kernel(const float *__restrict__ in, int ldi, int cin, const float *__restrict__ w /*[k3][cin][cout]*/, int cout,
-                        const int *__restrict__ nbr, int n_out, int k3, const float *__restrict__ bias, int relu,
-                        float *__restrict__ out, int ldo) {
-    extern __shared__ float s_w[];
-    for (int e = threadIdx.x; e < k3 * cin * cout; e += kStemThreads) s_w[e] = __ldg(w + e);
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int nj = cout / 32;   // <= 4
-    for (int r = blockIdx.x * (kStemThreads / 32) + (threadIdx.x >> 5); r < n_out; r += gridDim.x * (kStemThreads / 32)) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k0 = 0; k0 < k3; k0 += 32) {
-            const int mine = k0 + lane < k3 ? __ldg(nbr + (size_t)r * k3 + k0 + lane) : -1;
-            unsigned m = __ballot_sync(0xffffffffu, mine >= 0);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int src = __shfl_sync(0xffffffffu, mine, b);
-                const float *x = in + (size_t)src * ldi;
-                const float *wk = s_w + (size_t)(k0 + b) * cin * cout;
-                for (int c = 0; c < cin; c++) {
-                    const float xv = __ldg(x + c);
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (j < nj) acc[j] = fmaf(xv, wk[c * cout + lane + 32 * j], acc[j]);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (j < nj) {
-                float o = acc[j] + (bias ? __ldg(bias + lane + 32 * j) : 0.f);
-                if (relu) o = fmaxf(o, 0.f);
-                out[(size_t)r * ldo + lane + 32 * j] = o;
-            }
-    }
-}
-
 // im2col of a small-width input: col[o, k*cin + c] = in[nbr[o,k], c] (0 where the neighbour is missing; the columns
 // beyond K^3*cin up to ldo are zero padding).  One thread per (row, offset): a warp writes 32*cin consecutive floats.
 // With it the 3-channel 5^3 stem (375 -> 384 columns) becomes a plain [N,384] x [384,32] product on the tensor cores.
@@ -122,23 +79,6 @@ extern "C" int cvb200_sc_run_program(const cvb200_sc_op *ops, int32_t n_ops, voi
             const int rc = launch_conv_persist(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, o.k3, o.bias, o.residual, o.ldr,
                                                o.relu, o.out, o.ldo, stream, 0, o.n_out_dev, o.decode);
             if (rc) return rc;
-        } else if (o.kind == CVB200_OP_CONV_SMALLCIN) {
-            CVB_REQUIRE(!o.n_out_dev && !o.decode, CVB200_EINVAL, "sc_run_program: op %d: a device-side row count / fused decode needs a tensor-core kind", i);
-            CVB_REQUIRE(o.cin >= 1 && o.cin <= 8 && o.cout % 32 == 0 && o.cout <= 128 && !o.residual, CVB200_EINVAL,
-                        "sc_run_program: op %d: small-cin convolution needs cin <= 8, cout in {32,64,96,128}, no residual", i);
-            const size_t smem = sizeof(float) * (size_t)o.k3 * o.cin * o.cout;
-            CVB_REQUIRE(smem <= 160 * 1024, CVB200_EINVAL, "sc_run_program: op %d: kernel does not fit shared memory", i);
-            static DeviceOnce once;
-            if (!once.done()) {
-                CVB_CUDA(cudaFuncSetAttribute(sc_conv_smallcin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                once.mark();
-            }
-            if (o.n_out > 0) {
-                const int blocks = (int)std::min<int64_t>(2 * kNumSMs, ceil_div(o.n_out, kStemThreads / 32));
-                sc_conv_smallcin_kernel<<<blocks, kStemThreads, smem, stream>>>(o.in, o.ldi, o.cin, o.w, o.cout, o.table, (int)o.n_out,
-                                                                               o.k3, o.bias, o.relu, o.out, o.ldo);
-                CVB_LAUNCH_CHECK("sc_conv_smallcin_kernel");
-            }
         } else if (o.kind == CVB200_OP_CONV_TC_GATHER4) {
             // 4-channel input gathered 8 neighbours per k-block: o.k3 = table width, o.cin = 32 * ceil(k3 / 8) = K of the weights
             const int rc = launch_conv_persist(o.in, o.n_in, o.ldi, o.cin, o.w, o.cout, o.table, o.n_out, 1, o.bias, o.residual, o.ldr, o.relu,

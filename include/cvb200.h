@@ -259,10 +259,9 @@ int cvb200_sc_build_maps(const int32_t *d_coords, int64_t n, int32_t stem_ksize,
  *   out[:, 0:cout) (row stride ldo) = [relu]( sum_k in[table[o,k], 0:cin) (row stride ldi) @ W[k] + bias + residual )
  * `in`, `out` and `residual` may point into column slices of wider buffers (that is how ME.cat,
  * utils/minkunet.py:153-177, costs nothing).  kind CVB200_OP_CONV_TC: tcgen05 path, w = [k3,cout,cin]
- * (pre-transposed, BatchNorm folded in), cin % 32 == 0, cout % 16 == 0;  kind CVB200_OP_CONV_SMALLCIN:
- * CUDA-core path for the 3-channel stem, w = [k3,cin,cout], cin <= 8, cout % 32 == 0. */
+ * (pre-transposed, BatchNorm folded in), cin % 32 == 0, cout % 16 == 0.  (Kind 1, a CUDA-core kernel for the 3-channel stem,
+ * was retired in round 2: the stem runs through CVB200_OP_CONV_TC_GATHER4.) */
 #define CVB200_OP_CONV_TC 0
-#define CVB200_OP_CONV_SMALLCIN 1
 #define CVB200_OP_IM2COL 2        /* out[o, k*cin + c] = in[table[o,k], c] (0 if missing / padding), ldo % cin == 0 */
 #define CVB200_OP_CONV_TC_GATHER4 3 /* tcgen05 convolution of a 4-channel input (ldi = 4; the 3-channel stem padded with a zero
                                    * channel): table [n_out, k3], w = [cout][K], K = cin = 32*ceil(k3/8), w[co][4*k + c]; the
